@@ -1,0 +1,135 @@
+/*
+ * shine_b200.h — C ABI of the B200-native (sm_100a) implementation of SHINE-mapping's per-point SDF
+ * training step.  Plain C: raw device pointers + sizes + a cudaStream_t passed as void*; no torch types.
+ *
+ * The reference (PRBonn/SHINE_mapping @ 0fbaf8a) is 100 % Python and has NO FFI boundary for this path:
+ * the path sits behind three Python call sites of the training loop (shine_batch.py:123 `query_feature`,
+ * :128 `Decoder.sdf`, :174 `sdf_bce_loss`, :209 `backward`).  Each entry point below names the reference
+ * interface it replaces (file:line, relative to the reference root).  INTEGRATION.md shows the ctypes
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - return 0 on success, a positive cudaError_t on a CUDA failure, a negative SHINE_ERR_* on a bad
+ *     argument / unsupported configuration.  shine_error_string() decodes either.
+ *   - all buffers are caller-owned device memory; nothing is allocated, freed or synchronised inside;
+ *     every call is asynchronous on `stream` and re-entrant.
+ *   - levels are described BOTTOM-UP like `FeatureOctree.hierarchical_indices`
+ *     (model/feature_octree.py:201-202): lv[0] is the leaf level `tree_level_world`.
+ *   - a voxel that is not in the level's node table is a MISS: its eight corner ids are -1, its feature
+ *     contribution is exactly 0 (the reference's zeroed "trash-bin" last row, model/feature_octree.py:76-81,
+ *     205-213,232-233) and it receives no gradient.
+ */
+#ifndef SHINE_B200_H_
+#define SHINE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SHINE_ABI_VERSION 1
+#define SHINE_MAX_LEVELS 8
+#define SHINE_HASH_SLOT_BYTES 64
+
+#define SHINE_OK 0
+#define SHINE_ERR_INVALID_ARG (-1)
+#define SHINE_ERR_UNSUPPORTED (-2)
+
+/* flags of shine_sdf_* calls */
+#define SHINE_FLAG_REDUCTION_SUM 1u   /* loss_reduction == "sum" (shine_incre.py:77-78); default mean   */
+#define SHINE_FLAG_WEIGHTED 2u        /* loss_weight_on (utils/loss.py:18-19): per-sample weight applied */
+#define SHINE_FLAG_TF32X1 4u          /* decoder contractions in plain TF32 (default: 3xTF32 ~ fp32)     */
+
+/* One featured level of the FeatureOctree (model/feature_octree.py:46-63). */
+typedef struct shine_level {
+    const void* hash_slots;   /* capacity x 64-byte slots {u64 morton key | i32 node | pad | i32 ids[8]}:
+                                 replaces nodes_lookup_tables[level] (dict morton -> 8 corner rows)      */
+    const float* features;    /* hier_features[k]: [rows, F] fp32, last row = trash-bin                  */
+    float* feature_grads;     /* same shape, accumulated into (+=); may be NULL when no grads are asked  */
+    uint32_t hash_capacity;   /* power of two                                                            */
+    int32_t rows;             /* N_l + 1                                                                 */
+    int32_t level;            /* octree level in world numbering (leaf = tree_level_world)               */
+    int32_t reserved;
+} shine_level;
+
+typedef struct shine_octree {
+    int32_t num_levels;       /* L = tree_level_feat, 1..SHINE_MAX_LEVELS                                */
+    int32_t feature_dim;      /* F = feature_dim (multiple of 4; fused sdf_* kernels need 8)             */
+    int32_t poly_interp;      /* poly_int_on: smoothstep 3d^2-2d^3 weights (model/feature_octree.py:176) */
+    int32_t reserved;
+    shine_level lv[SHINE_MAX_LEVELS];
+} shine_octree;
+
+/* Geometry decoder (model/decoder.py:29-36): Linear(F,H)+ReLU, Linear(H,H)+ReLU, Linear(H,1);
+ * PyTorch (out,in) row-major weights.  Bias pointers may be NULL (geo_mlp_bias_on False).
+ * g* are gradient buffers (+=); all NULL == frozen decoder (utils/tools.py:188-191). */
+typedef struct shine_decoder {
+    const float *w1, *b1, *w2, *b2, *w3, *b3;
+    float *gw1, *gb1, *gw2, *gb2, *gw3, *gb3;
+    int32_t in_dim;           /* F  (8)  */
+    int32_t hidden;           /* H  (32) */
+    int32_t mlp_level;        /* 2       */
+    int32_t reserved;
+} shine_decoder;
+
+int shine_abi_version(void);
+const char* shine_error_string(int code);
+
+/* Build / extend the device node table of one level.  Replaces the Python dict fill at
+ * model/feature_octree.py:162-166.  `slots` must have been memset to 0xFF (empty) before the first
+ * insert.  keys: [n] int64 Morton codes, corner_ids: [n,8] int32 rows, node_base: ordinal of keys[0]. */
+int shine_hash_insert(void* slots, uint32_t capacity, const int64_t* keys, const int32_t* corner_ids,
+                      int64_t n, int32_t node_base, void* stream);
+
+/* kal.ops.spc.quantize_points + points_to_morton (call sites model/feature_octree.py:203-204):
+ * coord [n,3] fp32 -> morton [n] int64 at `level`. */
+int shine_points_to_morton(const float* coord, int64_t n, int32_t level, int64_t* morton, void* stream);
+
+/* FeatureOctree.get_indices (model/feature_octree.py:199-218): out_idx [L, n, 8] int64, level-major
+ * bottom-up, -1 x8 on a miss. */
+int shine_get_indices(const shine_octree* oct, const float* coord, int64_t n, int64_t* out_idx, void* stream);
+
+/* FeatureOctree.query_feature (model/feature_octree.py:237-244; interpolat :172-196, blend :222-234):
+ * out_feat [n, F] fp32 = sum over levels of the 8-corner blend. */
+int shine_query_fwd(const shine_octree* oct, const float* coord, int64_t n, float* out_feat, void* stream);
+
+/* autograd of the above (the index_put_(accumulate=True) of shine_batch.py:209):
+ * lv[i].feature_grads[id] += w_c * dfeat[p]  for every hit corner. */
+int shine_query_bwd(const shine_octree* oct, const float* coord, int64_t n, const float* dfeat, void* stream);
+
+/* query_feature -> Decoder.sdf (model/decoder.py:49-63) fused, forward only (the mesher's query,
+ * utils/mesher.py:60-72).  out_pred [n].  out_mask (optional, may be NULL) [n] uint8 = voxel present at
+ * lv[mask_level] (utils/mesher.py:82-89). */
+int shine_sdf_infer(const shine_octree* oct, const shine_decoder* dec, const float* coord, int64_t n,
+                    float* out_pred, uint8_t* out_mask, int32_t mask_level, uint32_t flags, void* stream);
+
+/* query_feature -> Decoder.sdf -> sdf_bce_loss (utils/loss.py:17-24), forward only.
+ * label [n], weight [n] or NULL, sigma = sigma_sigmoid (shine_batch.py:87).
+ * out_loss [1] fp32 is ACCUMULATED (+=): caller zeroes it.  loss_scale multiplies every per-point term
+ * (1/N_global for "mean", 1 for "sum"). */
+int shine_sdf_bce_fwd(const shine_octree* oct, const shine_decoder* dec, const float* coord,
+                      const float* label, const float* weight, int64_t n, float sigma, float loss_scale,
+                      float* out_pred, float* out_loss, uint32_t flags, void* stream);
+
+/* The whole training step shine_batch.py:123-209 in ONE pass: forward, loss and the backward that
+ * scatter-adds into lv[i].feature_grads and dec->g*.  d_loss: device scalar dL/dloss (NULL == 1).
+ * out_pred / out_loss may be NULL (pure backward == "recompute" mode for a separate autograd backward). */
+int shine_sdf_bce_step(const shine_octree* oct, const shine_decoder* dec, const float* coord,
+                       const float* label, const float* weight, int64_t n, float sigma, float loss_scale,
+                       const float* d_loss, float* out_pred, float* out_loss, uint32_t flags, void* stream);
+
+/* Dense Adam (utils/tools.py:78-79: betas (0.9,0.99), eps 1e-15, weight decay as L2 on grads) over up to
+ * SHINE_ADAM_MAX_TENSORS tensors in one launch — shine_batch.py:210 `opt.step()`. */
+#define SHINE_ADAM_MAX_TENSORS 16
+typedef struct shine_adam_tensor {
+    float* param; float* grad; float* exp_avg; float* exp_avg_sq;
+    int64_t numel; float lr; float weight_decay;
+} shine_adam_tensor;
+int shine_adam_step(const shine_adam_tensor* tensors, int32_t count, float beta1, float beta2, float eps,
+                    int32_t step, int32_t zero_grad, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHINE_B200_H_ */

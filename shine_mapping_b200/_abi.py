@@ -1,0 +1,106 @@
+"""ctypes binding of the C ABI in include/shine_b200.h (csrc/libshine_b200.so).
+
+There is no fallback: if the library is missing or a call fails, an exception is raised.  The library is
+built in-tree by `__graft_entry__.build()` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libshine_b200.so")
+
+MAX_LEVELS = 8
+HASH_SLOT_BYTES = 64
+ADAM_MAX_TENSORS = 16
+FLAG_REDUCTION_SUM = 1
+FLAG_WEIGHTED = 2
+FLAG_TF32X1 = 4
+
+
+class ShineLevel(C.Structure):
+    _fields_ = [("hash_slots", C.c_void_p), ("features", C.c_void_p), ("feature_grads", C.c_void_p),
+                ("hash_capacity", C.c_uint32), ("rows", C.c_int32), ("level", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ShineOctree(C.Structure):
+    _fields_ = [("num_levels", C.c_int32), ("feature_dim", C.c_int32), ("poly_interp", C.c_int32),
+                ("reserved", C.c_int32), ("lv", ShineLevel * MAX_LEVELS)]
+
+
+class ShineDecoder(C.Structure):
+    _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+                ("w3", C.c_void_p), ("b3", C.c_void_p),
+                ("gw1", C.c_void_p), ("gb1", C.c_void_p), ("gw2", C.c_void_p), ("gb2", C.c_void_p),
+                ("gw3", C.c_void_p), ("gb3", C.c_void_p),
+                ("in_dim", C.c_int32), ("hidden", C.c_int32), ("mlp_level", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ShineAdamTensor(C.Structure):
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_int64), ("lr", C.c_float), ("weight_decay", C.c_float)]
+
+
+# name -> (restype, argtypes); every symbol declared in include/shine_b200.h
+_vp, _i64, _i32, _u32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_float
+_OCT, _DEC = C.POINTER(ShineOctree), C.POINTER(ShineDecoder)
+SYMBOLS = {
+    "shine_abi_version": (C.c_int, []),
+    "shine_error_string": (C.c_char_p, [C.c_int]),
+    "shine_hash_insert": (C.c_int, [_vp, _u32, _vp, _vp, _i64, _i32, _vp]),
+    "shine_points_to_morton": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
+    "shine_get_indices": (C.c_int, [_OCT, _vp, _i64, _vp, _vp]),
+    "shine_query_fwd": (C.c_int, [_OCT, _vp, _i64, _vp, _vp]),
+    "shine_query_bwd": (C.c_int, [_OCT, _vp, _i64, _vp, _vp]),
+    "shine_sdf_infer": (C.c_int, [_OCT, _DEC, _vp, _i64, _vp, _vp, _i32, _u32, _vp]),
+    "shine_sdf_bce_fwd": (C.c_int, [_OCT, _DEC, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _u32, _vp]),
+    "shine_sdf_bce_step": (C.c_int, [_OCT, _DEC, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp, _u32, _vp]),
+    "shine_adam_step": (C.c_int, [C.POINTER(ShineAdamTensor), _i32, _f32, _f32, _f32, _i32, _i32, _vp]),
+}
+
+_lib = None
+
+
+class ShineB200Error(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    """Load csrc/libshine_b200.so (once).  Raises if it has not been built — no CPU / eager fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ShineB200Error(
+                f"{LIB_PATH} is missing: build the sm_100a kernels first (python -c 'import __graft_entry__ as g; "
+                "g.build()').  shine_mapping_b200 has no CPU or eager fallback for the hot path.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SYMBOLS.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = restype, argtypes
+        if handle.shine_abi_version() != 1:
+            raise ShineB200Error("libshine_b200.so ABI version mismatch; rebuild")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().shine_error_string(rc).decode()
+        raise ShineB200Error(f"{what} failed: {msg} (code {rc})")
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise ShineB200Error(
+            f"{what}: tensor is on {t.device}; the hot path runs only as sm_100a CUDA kernels (no CPU fallback)")
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

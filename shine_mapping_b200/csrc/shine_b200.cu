@@ -1,0 +1,985 @@
+// shine_b200.cu — hand-written sm_100a kernels + the C ABI of include/shine_b200.h.
+//
+// Hot path (reference PRBonn/SHINE_mapping, shine_batch.py:123-209):
+//   FeatureOctree.query_feature  (model/feature_octree.py:199-244)   Morton hash walk + 8-corner blend, L levels
+//   Decoder.sdf                  (model/decoder.py:49-63)            8 -> 32 -> 32 -> 1 MLP
+//   sdf_bce_loss                 (utils/loss.py:17-24)               BCE-with-logits vs sigmoid(label/sigma)
+//   cur_loss.backward()          (shine_batch.py:209)                scatter-add into corner table + decoder grads
+//
+// Work decomposition of every per-point kernel here: a warp owns a TILE of 16 points (the M of
+// mma.m16n8k8).  Lane (g = lane>>2, t = lane&3) owns point  g + 8*(t&1)  and feature half  t>>1
+// (4 of the F=8 channels = one 16-byte half of a 32-byte table row).  The two lanes that share a row
+// are served by the same 32-byte sector, so every sector that comes back from L2/HBM is fully used.
+// That "row-half" layout converts to / from the mma A-fragment / C-fragment layouts with two
+// shfl.xor(1) each (see to_afrag / from_cfrag), so activations never touch shared memory in the forward.
+//
+// Built with: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see __graft_entry__.build()).
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "shine_b200.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------
+// constants / small helpers
+// ------------------------------------------------------------------------------------------------------
+
+constexpr int kTile = 16;          // points per warp tile
+constexpr int kF = 8;              // fused path: feature_dim
+constexpr int kH = 32;             // fused path: hidden width
+constexpr int kWS = 40;            // padded row stride (floats) of 32-wide smem matrices: conflict-free frags
+constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+struct __align__(64) HashSlot {
+    unsigned long long key;   // Morton code of the voxel, kEmptyKey when free
+    int32_t node;             // insertion ordinal (diagnostics)
+    int32_t pad[5];
+    int32_t ids[8];           // rows of the 8 corners in the level's feature table (second 32-B sector)
+};
+static_assert(sizeof(HashSlot) == SHINE_HASH_SLOT_BYTES, "slot must be 64 bytes");
+
+__host__ __device__ __forceinline__ uint32_t hash_key(unsigned long long k) {
+    k ^= k >> 31;
+    k *= 0x9E3779B97F4A7C15ull;
+    k ^= k >> 29;
+    k *= 0xBF58476D1CE4E5B9ull;
+    k ^= k >> 32;
+    return (uint32_t)k;
+}
+
+// bit i of v -> bit 3i (16 significant bits, as kaolin's int16 coordinates)
+__device__ __forceinline__ unsigned long long spread3(uint32_t v) {
+    unsigned long long x = v & 0xFFFFull;
+    x = (x | (x << 16)) & 0x0000FF0000FFull;
+    x = (x | (x << 8)) & 0x00F00F00F00Full;
+    x = (x | (x << 4)) & 0x0C30C30C30C3ull;
+    x = (x | (x << 2)) & 0x249249249249ull;
+    return x;
+}
+
+// kal.ops.spc.quantize_points (model/feature_octree.py:203): floor(clamp(res*(x+1)/2, 0, res-1)), fp32 op order kept
+__device__ __forceinline__ uint32_t quantize1(float x, float res) {
+    float v = __fmul_rn(__fmul_rn(res, __fadd_rn(x, 1.0f)), 0.5f);
+    v = fminf(fmaxf(v, 0.0f), res - 1.0f);
+    return (uint32_t)(int)floorf(v);
+}
+
+// kal.ops.spc.points_to_morton (model/feature_octree.py:204): x -> bit 3i+2, y -> 3i+1, z -> 3i
+__device__ __forceinline__ unsigned long long morton_of(float x, float y, float z, int level) {
+    const float res = (float)(1u << level);
+    return (spread3(quantize1(x, res)) << 2) | (spread3(quantize1(y, res)) << 1) | spread3(quantize1(z, res));
+}
+
+// FeatureOctree.interpolat (model/feature_octree.py:172-185): per-axis blend factor at `level`
+__device__ __forceinline__ float axis_t(float x, float res, bool poly) {
+    const float c = __fmul_rn(res, __fmaf_rn(x, 0.5f, 0.5f));   // x*0.5 is exact, so the fma rounds like mul+add
+    const float d = c - truncf(c);                              // torch.frac
+    if (!poly) return d;
+    const float d2 = __fmul_rn(d, d);
+    const float d3 = __fmul_rn(d2, d);
+    return __fsub_rn(__fmul_rn(3.0f, d2), __fmul_rn(2.0f, d3));
+}
+
+struct Blend {   // the 8 weights of model/feature_octree.py:186-193, corner c = (x bit2, y bit1, z bit0)
+    float tx, ty, tz, ux, uy, uz;
+    __device__ __forceinline__ void init(float x, float y, float z, int level, bool poly) {
+        const float res = (float)(1u << level);
+        tx = axis_t(x, res, poly); ty = axis_t(y, res, poly); tz = axis_t(z, res, poly);
+        ux = __fsub_rn(1.0f, tx); uy = __fsub_rn(1.0f, ty); uz = __fsub_rn(1.0f, tz);
+    }
+    __device__ __forceinline__ float w(int c) const {
+        const float a = (c & 4) ? tx : ux, b = (c & 2) ? ty : uy, d = (c & 1) ? tz : uz;
+        return __fmul_rn(__fmul_rn(a, b), d);
+    }
+};
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ int4 ldg_i4(const int32_t* p) {
+    return __ldg(reinterpret_cast<const int4*>(p));
+}
+__device__ __forceinline__ void red_add_f4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// nodes_lookup_tables[level].get(morton, [-1]*8)  (model/feature_octree.py:205-209) as an open-addressing probe.
+// Returns the slot index or -1.  The first probe loads key speculatively together with the caller's id loads.
+__device__ __forceinline__ int probe_slot(const HashSlot* __restrict__ slots, uint32_t mask, unsigned long long key) {
+    uint32_t h = hash_key(key) & mask;
+#pragma unroll 1
+    for (uint32_t n = 0; n <= mask; ++n) {
+        const unsigned long long k = __ldg(&slots[h].key);
+        if (k == key) return (int)h;
+        if (k == kEmptyKey) return -1;
+        h = (h + 1) & mask;
+    }
+    return -1;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// hash build (model/feature_octree.py:162-166)
+// ------------------------------------------------------------------------------------------------------
+
+__global__ void hash_insert_kernel(HashSlot* __restrict__ slots, uint32_t mask, const int64_t* __restrict__ keys,
+                                   const int32_t* __restrict__ corner_ids, int64_t n, int32_t node_base) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long key = (unsigned long long)keys[i];
+    uint32_t h = hash_key(key) & mask;
+    for (uint32_t it = 0; it <= mask; ++it) {
+        const unsigned long long prev = atomicCAS(&slots[h].key, kEmptyKey, key);
+        if (prev == kEmptyKey || prev == key) {
+            slots[h].node = node_base + (int32_t)i;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) slots[h].ids[c] = corner_ids[i * 8 + c];
+            return;
+        }
+        h = (h + 1) & mask;
+    }
+}
+
+__global__ void points_to_morton_kernel(const float* __restrict__ coord, int64_t n, int level,
+                                        int64_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = (int64_t)morton_of(coord[3 * i], coord[3 * i + 1], coord[3 * i + 2], level);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// get_indices (model/feature_octree.py:199-218): one thread per (point, level)
+// ------------------------------------------------------------------------------------------------------
+
+__global__ void get_indices_kernel(const __grid_constant__ shine_octree oct, const float* __restrict__ coord,
+                                   int64_t n, int64_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lvl = blockIdx.y;
+    if (i >= n) return;
+    const shine_level& lv = oct.lv[lvl];
+    const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
+    const unsigned long long key = morton_of(coord[3 * i], coord[3 * i + 1], coord[3 * i + 2], lv.level);
+    const int s = probe_slot(slots, lv.hash_capacity - 1, key);
+    longlong2* dst = reinterpret_cast<longlong2*>(out + ((int64_t)lvl * n + i) * 8);
+    if (s < 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dst[c] = make_longlong2(-1, -1);
+    } else {
+        const int4 a = ldg_i4(slots[s].ids), b = ldg_i4(slots[s].ids + 4);
+        dst[0] = make_longlong2(a.x, a.y); dst[1] = make_longlong2(a.z, a.w);
+        dst[2] = make_longlong2(b.x, b.y); dst[3] = make_longlong2(b.z, b.w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// query_feature forward / backward for any F = 4*LP (LP lanes share one point)
+// ------------------------------------------------------------------------------------------------------
+
+template <int LP>
+__global__ void __launch_bounds__(256) query_fwd_kernel(const __grid_constant__ shine_octree oct,
+                                                        const float* __restrict__ coord, int64_t n,
+                                                        float* __restrict__ out) {
+    constexpr int F = 4 * LP;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t p = gtid / LP;
+    const int part = (int)(gtid % LP);
+    if (p >= n) return;
+    const float x = coord[3 * p], y = coord[3 * p + 1], z = coord[3 * p + 2];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < oct.num_levels; ++i) {
+        const shine_level& lv = oct.lv[i];
+        const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
+        const int s = probe_slot(slots, lv.hash_capacity - 1, morton_of(x, y, z, lv.level));
+        if (s < 0) continue;
+        const int4 ia = ldg_i4(slots[s].ids), ib = ldg_i4(slots[s].ids + 4);
+        const int ids[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
+        float4 v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = ldg_f4(lv.features + (int64_t)ids[c] * F + 4 * part);
+        Blend b; b.init(x, y, z, lv.level, oct.poly_interp != 0);
+        float4 lsum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float w = b.w(c);
+            lsum.x = fmaf(w, v[c].x, lsum.x); lsum.y = fmaf(w, v[c].y, lsum.y);
+            lsum.z = fmaf(w, v[c].z, lsum.z); lsum.w = fmaf(w, v[c].w, lsum.w);
+        }
+        acc.x += lsum.x; acc.y += lsum.y; acc.z += lsum.z; acc.w += lsum.w;
+    }
+    *reinterpret_cast<float4*>(out + p * F + 4 * part) = acc;
+}
+
+template <int LP>
+__global__ void __launch_bounds__(256) query_bwd_kernel(const __grid_constant__ shine_octree oct,
+                                                        const float* __restrict__ coord, int64_t n,
+                                                        const float* __restrict__ dfeat) {
+    constexpr int F = 4 * LP;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t p = gtid / LP;
+    const int part = (int)(gtid % LP);
+    if (p >= n) return;
+    const float x = coord[3 * p], y = coord[3 * p + 1], z = coord[3 * p + 2];
+    const float4 d = ldg_f4(dfeat + p * F + 4 * part);
+    for (int i = 0; i < oct.num_levels; ++i) {
+        const shine_level& lv = oct.lv[i];
+        const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
+        const int s = probe_slot(slots, lv.hash_capacity - 1, morton_of(x, y, z, lv.level));
+        if (s < 0) continue;
+        const int4 ia = ldg_i4(slots[s].ids), ib = ldg_i4(slots[s].ids + 4);
+        const int ids[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
+        Blend b; b.init(x, y, z, lv.level, oct.poly_interp != 0);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float w = b.w(c);
+            red_add_f4(lv.feature_grads + (int64_t)ids[c] * F + 4 * part, w * d.x, w * d.y, w * d.z, w * d.w);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// tensor-core helpers: mma.sync m16n8k8 TF32, fp32 accumulate, optional 3xTF32 error compensation
+// ------------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    hi = f2tf32(x);
+    lo = f2tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// A operand: fp32 values in A-fragment order, split on demand.  NTF == 3: D += Al*Bh + Ah*Bl + Ah*Bh.
+template <int NTF>
+struct AFrag {
+    uint32_t hi[4], lo[4];
+    __device__ __forceinline__ void set(float a0, float a1, float a2, float a3) {
+        if (NTF == 3) {
+            split_tf32(a0, hi[0], lo[0]); split_tf32(a1, hi[1], lo[1]);
+            split_tf32(a2, hi[2], lo[2]); split_tf32(a3, hi[3], lo[3]);
+        } else {
+            hi[0] = f2tf32(a0); hi[1] = f2tf32(a1); hi[2] = f2tf32(a2); hi[3] = f2tf32(a3);
+        }
+    }
+};
+template <int NTF>
+__device__ __forceinline__ void mma3(float (&d)[4], const AFrag<NTF>& a, uint2 bh, uint2 bl) {
+    if (NTF == 3) {
+        mma_tf32(d, a.lo, bh.x, bh.y);
+        mma_tf32(d, a.hi, bl.x, bl.y);
+    }
+    mma_tf32(d, a.hi, bh.x, bh.y);
+}
+
+// row-half layout (this lane: 4 channels of its own point) -> A fragment of the 16x8 tile.
+// k-slot t <-> channel 2t, k-slot t+4 <-> channel 2t+1 (the B fragments use the same permutation).
+__device__ __forceinline__ void to_afrag(const float (&v)[4], int odd, float (&a)[4]) {
+    const float s0 = odd ? v[0] : v[2], s1 = odd ? v[1] : v[3];
+    const float r0 = __shfl_xor_sync(kFull, s0, 1), r1 = __shfl_xor_sync(kFull, s1, 1);
+    if (!odd) { a[0] = v[0]; a[2] = v[1]; a[1] = r0; a[3] = r1; }
+    else      { a[0] = r0;   a[2] = r1;   a[1] = v[2]; a[3] = v[3]; }
+}
+// C fragment of a 16x8 tile (rows g,g+8; cols 2t,2t+1) -> row-half layout
+__device__ __forceinline__ void from_cfrag(const float (&c)[4], int odd, float (&v)[4]) {
+    const float s0 = odd ? c[0] : c[2], s1 = odd ? c[1] : c[3];
+    const float r0 = __shfl_xor_sync(kFull, s0, 1), r1 = __shfl_xor_sync(kFull, s1, 1);
+    if (!odd) { v[0] = c[0]; v[1] = c[1]; v[2] = r0; v[3] = r1; }
+    else      { v[0] = r0;   v[1] = r1;   v[2] = c[2]; v[3] = c[3]; }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// the fused kernel: hash walk + gather + blend + MLP (+ BCE loss) (+ full backward with scatter-add)
+// ------------------------------------------------------------------------------------------------------
+
+struct StepParams {
+    shine_octree oct;
+    shine_decoder dec;
+    const float* coord;
+    const float* label;
+    const float* weight;     // nullable (ignored unless weighted)
+    const float* d_loss;     // nullable device scalar
+    float* pred;             // nullable
+    float* loss;             // nullable, accumulated
+    uint8_t* mask;           // nullable (infer only)
+    int64_t n;
+    int32_t num_tiles;
+    int32_t mask_level;
+    float sigma;
+    float loss_scale;
+    int32_t weighted;
+};
+
+// shared-memory plan (floats).  Weight matrices are pre-split into tf32 hi / lo words.
+struct SmemPlan {
+    static constexpr int W1 = 0;                       // [32][8]   W1[n][k]
+    static constexpr int W1T = W1 + 2 * kH * kF;       // [8][kWS]  W1T[k][n]
+    static constexpr int W2 = W1T + 2 * kF * kWS;      // [32][kWS] W2[n][k]
+    static constexpr int W2T = W2 + 2 * kH * kWS;      // [32][kWS] W2T[k][n]
+    static constexpr int B1 = W2T + 2 * kH * kWS;      // [32]
+    static constexpr int B2 = B1 + kH;
+    static constexpr int W3 = B2 + kH;
+    static constexpr int B3 = W3 + kH;                 // [1] (+3 pad)
+    static constexpr int RED = B3 + 4;                 // block accumulator for decoder grads [1377 -> 1380]
+    static constexpr int kDecGradFloats = kH * kF + kH + kH * kH + kH + kH + 1;   // 1377
+    static constexpr int STAGE = RED + 1380;           // per-warp staging: 2 x [16][kWS] + [16][8]
+    static constexpr int kStagePerWarp = 2 * kTile * kWS + kTile * kF;
+};
+
+template <int NTF, bool TRAIN, bool DEC_GRAD, int LMAX>
+__global__ void __launch_bounds__(256) sdf_fused_kernel(const __grid_constant__ StepParams P) {
+    extern __shared__ __align__(16) float smem[];
+    uint32_t* smu = reinterpret_cast<uint32_t*>(smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3, odd = t & 1, half = t >> 1;
+    constexpr int kWarps = 8;
+
+    // ---- stage decoder weights (hi/lo split) into shared memory --------------------------------------
+    for (int i = tid; i < kH * kF; i += blockDim.x) {
+        const int nrow = i / kF, k = i % kF;
+        uint32_t hi, lo; split_tf32(P.dec.w1[i], hi, lo);
+        smu[SmemPlan::W1 + i] = hi; smu[SmemPlan::W1 + kH * kF + i] = lo;
+        smu[SmemPlan::W1T + k * kWS + nrow] = hi; smu[SmemPlan::W1T + kF * kWS + k * kWS + nrow] = lo;
+    }
+    for (int i = tid; i < kH * kH; i += blockDim.x) {
+        const int nrow = i / kH, k = i % kH;
+        uint32_t hi, lo; split_tf32(P.dec.w2[i], hi, lo);
+        smu[SmemPlan::W2 + nrow * kWS + k] = hi; smu[SmemPlan::W2 + kH * kWS + nrow * kWS + k] = lo;
+        smu[SmemPlan::W2T + k * kWS + nrow] = hi; smu[SmemPlan::W2T + kH * kWS + k * kWS + nrow] = lo;
+    }
+    if (tid < kH) {
+        smem[SmemPlan::B1 + tid] = P.dec.b1 ? P.dec.b1[tid] : 0.f;
+        smem[SmemPlan::B2 + tid] = P.dec.b2 ? P.dec.b2[tid] : 0.f;
+        smem[SmemPlan::W3 + tid] = P.dec.w3[tid];
+    }
+    if (tid == 0) smem[SmemPlan::B3] = P.dec.b3 ? P.dec.b3[0] : 0.f;
+    if (DEC_GRAD) for (int i = tid; i < 1380; i += blockDim.x) smem[SmemPlan::RED + i] = 0.f;
+    __syncthreads();
+
+    const bool poly = P.oct.poly_interp != 0;
+    const int L = P.oct.num_levels;
+    const float up = (TRAIN && P.d_loss) ? __ldg(P.d_loss) : 1.0f;
+    const float gscale = P.loss_scale * up;
+
+    // persistent decoder-gradient accumulators (C-fragment layout), reduced once at the end
+    float dW2[2][4][4], dW1[2][4], db2p[4][2], db1p[4][2], dw3p[4][2], db3p = 0.f;
+    if (DEC_GRAD) {
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) { dW2[a][b][0] = dW2[a][b][1] = dW2[a][b][2] = dW2[a][b][3] = 0.f; }
+            dW1[a][0] = dW1[a][1] = dW1[a][2] = dW1[a][3] = 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { db2p[j][0] = db2p[j][1] = db1p[j][0] = db1p[j][1] = dw3p[j][0] = dw3p[j][1] = 0.f; }
+    }
+    float loss_acc = 0.f;
+
+    float* stage = smem + SmemPlan::STAGE + warp * SmemPlan::kStagePerWarp;   // only touched when DEC_GRAD
+    float* stA = stage;                       // [16][kWS]
+    float* stB = stage + kTile * kWS;         // [16][kWS]
+    float* stX = stage + 2 * kTile * kWS;     // [16][8]
+
+    const int warp_global = blockIdx.x * kWarps + warp;
+    const int warp_stride = gridDim.x * kWarps;
+
+    for (int tile = warp_global; tile < P.num_tiles; tile += warp_stride) {
+        const int64_t base = (int64_t)tile * kTile;
+        const int64_t myp = base + g + 8 * odd;
+        const bool valid = myp < P.n;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (valid) { x = __ldg(P.coord + 3 * myp); y = __ldg(P.coord + 3 * myp + 1); z = __ldg(P.coord + 3 * myp + 2); }
+
+        // ---- hash walk + gather + blend (model/feature_octree.py:199-234) ----------------------------
+        int slot[LMAX];
+        float feat[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < LMAX; ++i) {
+            slot[i] = -1;
+            if (i < L && valid) {
+                const shine_level& lv = P.oct.lv[i];
+                const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
+                slot[i] = probe_slot(slots, lv.hash_capacity - 1, morton_of(x, y, z, lv.level));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < LMAX; ++i) {
+            if (i < L && slot[i] >= 0) {
+                const shine_level& lv = P.oct.lv[i];
+                const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
+                const int4 ia = ldg_i4(slots[slot[i]].ids), ib = ldg_i4(slots[slot[i]].ids + 4);
+                const float* fb = lv.features + 4 * half;
+                float4 v[8];
+                v[0] = ldg_f4(fb + (int64_t)ia.x * kF); v[1] = ldg_f4(fb + (int64_t)ia.y * kF);
+                v[2] = ldg_f4(fb + (int64_t)ia.z * kF); v[3] = ldg_f4(fb + (int64_t)ia.w * kF);
+                v[4] = ldg_f4(fb + (int64_t)ib.x * kF); v[5] = ldg_f4(fb + (int64_t)ib.y * kF);
+                v[6] = ldg_f4(fb + (int64_t)ib.z * kF); v[7] = ldg_f4(fb + (int64_t)ib.w * kF);
+                Blend b; b.init(x, y, z, lv.level, poly);
+                float4 ls = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float w = b.w(c);
+                    ls.x = fmaf(w, v[c].x, ls.x); ls.y = fmaf(w, v[c].y, ls.y);
+                    ls.z = fmaf(w, v[c].z, ls.z); ls.w = fmaf(w, v[c].w, ls.w);
+                }
+                feat[0] += ls.x; feat[1] += ls.y; feat[2] += ls.z; feat[3] += ls.w;
+            }
+        }
+        if (!TRAIN && P.mask) {
+            bool present = false;
+#pragma unroll
+            for (int i = 0; i < LMAX; ++i) present = (i == P.mask_level) ? (slot[i] >= 0) : present;
+            if (half == 0 && valid) P.mask[myp] = (uint8_t)present;
+        }
+
+        // ---- Decoder.sdf forward (model/decoder.py:49-63) on tensor cores -----------------------------
+        AFrag<NTF> ax;
+        {
+            float a[4]; to_afrag(feat, odd, a);
+            ax.set(a[0], a[1], a[2], a[3]);
+        }
+        float h1[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float bA = smem[SmemPlan::B1 + 8 * j + 2 * t], bB = smem[SmemPlan::B1 + 8 * j + 2 * t + 1];
+            float c[4] = {bA, bB, bA, bB};
+            const int off = (8 * j + g) * kF + 2 * t;
+            const uint2 bh = *reinterpret_cast<const uint2*>(smu + SmemPlan::W1 + off);
+            const uint2 bl = *reinterpret_cast<const uint2*>(smu + SmemPlan::W1 + kH * kF + off);
+            mma3<NTF>(c, ax, bh, bl);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) h1[j][r] = fmaxf(c[r], 0.f);
+        }
+        float h2[4][4];
+        {
+            AFrag<NTF> ah[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) ah[kk].set(h1[kk][0], h1[kk][2], h1[kk][1], h1[kk][3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float bA = smem[SmemPlan::B2 + 8 * j + 2 * t], bB = smem[SmemPlan::B2 + 8 * j + 2 * t + 1];
+                float c[4] = {bA, bB, bA, bB};
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int off = (8 * j + g) * kWS + 8 * kk + 2 * t;
+                    const uint2 bh = *reinterpret_cast<const uint2*>(smu + SmemPlan::W2 + off);
+                    const uint2 bl = *reinterpret_cast<const uint2*>(smu + SmemPlan::W2 + kH * kWS + off);
+                    mma3<NTF>(c, ah[kk], bh, bl);
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) h2[j][r] = fmaxf(c[r], 0.f);
+            }
+        }
+        float w3a[4], w3b[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { w3a[j] = smem[SmemPlan::W3 + 8 * j + 2 * t]; w3b[j] = smem[SmemPlan::W3 + 8 * j + 2 * t + 1]; }
+        float p0 = 0.f, p8 = 0.f;   // rows g and g+8
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            p0 = fmaf(h2[j][0], w3a[j], p0); p0 = fmaf(h2[j][1], w3b[j], p0);
+            p8 = fmaf(h2[j][2], w3a[j], p8); p8 = fmaf(h2[j][3], w3b[j], p8);
+        }
+        p0 += __shfl_xor_sync(kFull, p0, 1); p0 += __shfl_xor_sync(kFull, p0, 2);
+        p8 += __shfl_xor_sync(kFull, p8, 1); p8 += __shfl_xor_sync(kFull, p8, 2);
+        const float b3 = smem[SmemPlan::B3];
+        p0 += b3; p8 += b3;
+        const float pown = odd ? p8 : p0;
+        if (P.pred && half == 0 && valid) P.pred[myp] = pown;
+
+        if (P.label == nullptr) continue;   // pure inference
+
+        // ---- sdf_bce_loss (utils/loss.py:17-24) + dL/dpred ---------------------------------------------
+        float dpo = 0.f;
+        if (valid) {
+            const float lab = __ldg(P.label + myp);
+            const float wgt = P.weighted ? fabsf(__ldg(P.weight + myp)) : 1.0f;   // shine_batch.py:172 abs()
+            const float zt = 1.0f / (1.0f + expf(-__fdiv_rn(lab, P.sigma)));       // sigmoid(label / sigma)
+            const float e = expf(-fabsf(pown));
+            const float li = fmaxf(pown, 0.f) - pown * zt + log1pf(e);
+            if (half == 0) loss_acc += wgt * li;
+            if (TRAIN) {
+                const float sg = pown >= 0.f ? 1.0f / (1.0f + e) : e / (1.0f + e);   // sigmoid(pred)
+                dpo = (sg - zt) * wgt * gscale;
+            }
+        }
+        if (!TRAIN) continue;
+
+        // ---- backward: MLP dgrad on tensor cores ------------------------------------------------------
+        const float dpx = __shfl_xor_sync(kFull, dpo, 1);
+        const float dp0 = odd ? dpx : dpo, dp8 = odd ? dpo : dpx;
+        float dh2[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            dh2[j][0] = h2[j][0] > 0.f ? dp0 * w3a[j] : 0.f; dh2[j][1] = h2[j][1] > 0.f ? dp0 * w3b[j] : 0.f;
+            dh2[j][2] = h2[j][2] > 0.f ? dp8 * w3a[j] : 0.f; dh2[j][3] = h2[j][3] > 0.f ? dp8 * w3b[j] : 0.f;
+            if (DEC_GRAD) {
+                dw3p[j][0] += dp0 * h2[j][0] + dp8 * h2[j][2]; dw3p[j][1] += dp0 * h2[j][1] + dp8 * h2[j][3];
+                db2p[j][0] += dh2[j][0] + dh2[j][2];           db2p[j][1] += dh2[j][1] + dh2[j][3];
+            }
+        }
+        if (DEC_GRAD && t == 0) db3p += dp0 + dp8;
+
+        float dh1[4][4];
+        {
+            AFrag<NTF> ad[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) ad[kk].set(dh2[kk][0], dh2[kk][2], dh2[kk][1], dh2[kk][3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int off = (8 * j + g) * kWS + 8 * kk + 2 * t;
+                    const uint2 bh = *reinterpret_cast<const uint2*>(smu + SmemPlan::W2T + off);
+                    const uint2 bl = *reinterpret_cast<const uint2*>(smu + SmemPlan::W2T + kH * kWS + off);
+                    mma3<NTF>(c, ad[kk], bh, bl);
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) dh1[j][r] = h1[j][r] > 0.f ? c[r] : 0.f;
+                if (DEC_GRAD) { db1p[j][0] += dh1[j][0] + dh1[j][2]; db1p[j][1] += dh1[j][1] + dh1[j][3]; }
+            }
+        }
+        float dxc[4] = {0.f, 0.f, 0.f, 0.f};
+        {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                AFrag<NTF> a; a.set(dh1[kk][0], dh1[kk][2], dh1[kk][1], dh1[kk][3]);
+                const int off = g * kWS + 8 * kk + 2 * t;
+                const uint2 bh = *reinterpret_cast<const uint2*>(smu + SmemPlan::W1T + off);
+                const uint2 bl = *reinterpret_cast<const uint2*>(smu + SmemPlan::W1T + kF * kWS + off);
+                mma3<NTF>(dxc, a, bh, bl);
+            }
+        }
+
+        // ---- backward: decoder weight grads (contraction over the tile's 16 points) -------------------
+        if (DEC_GRAD) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                *reinterpret_cast<float2*>(stA + g * kWS + 8 * j + 2 * t) = make_float2(dh2[j][0], dh2[j][1]);
+                *reinterpret_cast<float2*>(stA + (g + 8) * kWS + 8 * j + 2 * t) = make_float2(dh2[j][2], dh2[j][3]);
+                *reinterpret_cast<float2*>(stB + g * kWS + 8 * j + 2 * t) = make_float2(h1[j][0], h1[j][1]);
+                *reinterpret_cast<float2*>(stB + (g + 8) * kWS + 8 * j + 2 * t) = make_float2(h1[j][2], h1[j][3]);
+            }
+            *reinterpret_cast<float4*>(stX + (g + 8 * odd) * kF + 4 * half) = make_float4(feat[0], feat[1], feat[2], feat[3]);
+            __syncwarp();
+            // dW2[n2][k1] += sum_rows dh2[row][n2] * h1[row][k1]
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                uint2 bh[4], bl[4];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const float b0 = stB[(8 * ks + t) * kWS + 8 * nt + g], b1 = stB[(8 * ks + t + 4) * kWS + 8 * nt + g];
+                    split_tf32(b0, bh[nt].x, bl[nt].x); split_tf32(b1, bh[nt].y, bl[nt].y);
+                }
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    AFrag<NTF> a;
+                    a.set(stA[(8 * ks + t) * kWS + 16 * mt + g], stA[(8 * ks + t) * kWS + 16 * mt + g + 8],
+                          stA[(8 * ks + t + 4) * kWS + 16 * mt + g], stA[(8 * ks + t + 4) * kWS + 16 * mt + g + 8]);
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) mma3<NTF>(dW2[mt][nt], a, bh[nt], bl[nt]);
+                }
+            }
+            __syncwarp();
+            // dW1[n1][ch] += sum_rows dh1[row][n1] * feat[row][ch]
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                *reinterpret_cast<float2*>(stA + g * kWS + 8 * j + 2 * t) = make_float2(dh1[j][0], dh1[j][1]);
+                *reinterpret_cast<float2*>(stA + (g + 8) * kWS + 8 * j + 2 * t) = make_float2(dh1[j][2], dh1[j][3]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                uint2 bh, bl;
+                split_tf32(stX[(8 * ks + t) * kF + g], bh.x, bl.x);
+                split_tf32(stX[(8 * ks + t + 4) * kF + g], bh.y, bl.y);
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    AFrag<NTF> a;
+                    a.set(stA[(8 * ks + t) * kWS + 16 * mt + g], stA[(8 * ks + t) * kWS + 16 * mt + g + 8],
+                          stA[(8 * ks + t + 4) * kWS + 16 * mt + g], stA[(8 * ks + t + 4) * kWS + 16 * mt + g + 8]);
+                    mma3<NTF>(dW1[mt], a, bh, bl);
+                }
+            }
+            __syncwarp();
+        }
+
+        // ---- backward: scatter-add into the corner-feature tables (index_put_ accumulate) -------------
+        float dx[4];
+        from_cfrag(dxc, odd, dx);
+#pragma unroll
+        for (int i = 0; i < LMAX; ++i) {
+            if (i < L && slot[i] >= 0) {
+                const shine_level& lv = P.oct.lv[i];
+                const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
+                const int4 ia = ldg_i4(slots[slot[i]].ids), ib = ldg_i4(slots[slot[i]].ids + 4);
+                const int ids[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
+                Blend b; b.init(x, y, z, lv.level, poly);
+                float* gb = lv.feature_grads + 4 * half;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float w = b.w(c);
+                    red_add_f4(gb + (int64_t)ids[c] * kF, w * dx[0], w * dx[1], w * dx[2], w * dx[3]);
+                }
+            }
+        }
+    }
+
+    // ---- epilogue: loss and decoder-gradient reductions --------------------------------------------------
+    if (P.loss && P.label) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(kFull, loss_acc, o);
+        if (lane == 0 && loss_acc != 0.f) atomicAdd(P.loss, loss_acc * P.loss_scale);
+    }
+    if (DEC_GRAD) {
+        float* red = smem + SmemPlan::RED;   // [gw1 256 | gb1 32 | gw2 1024 | gb2 32 | gw3 32 | gb3 1]
+        constexpr int oW1 = 0, oB1 = 256, oW2 = 288, oB2 = 1312, oW3 = 1344, oB3 = 1376;
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                atomicAdd(red + oW2 + (16 * mt + g) * kH + 8 * nt + 2 * t, dW2[mt][nt][0]);
+                atomicAdd(red + oW2 + (16 * mt + g) * kH + 8 * nt + 2 * t + 1, dW2[mt][nt][1]);
+                atomicAdd(red + oW2 + (16 * mt + g + 8) * kH + 8 * nt + 2 * t, dW2[mt][nt][2]);
+                atomicAdd(red + oW2 + (16 * mt + g + 8) * kH + 8 * nt + 2 * t + 1, dW2[mt][nt][3]);
+            }
+            atomicAdd(red + oW1 + (16 * mt + g) * kF + 2 * t, dW1[mt][0]);
+            atomicAdd(red + oW1 + (16 * mt + g) * kF + 2 * t + 1, dW1[mt][1]);
+            atomicAdd(red + oW1 + (16 * mt + g + 8) * kF + 2 * t, dW1[mt][2]);
+            atomicAdd(red + oW1 + (16 * mt + g + 8) * kF + 2 * t + 1, dW1[mt][3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                float a = db1p[j][q], b = db2p[j][q], c = dw3p[j][q];
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    a += __shfl_xor_sync(kFull, a, o); b += __shfl_xor_sync(kFull, b, o); c += __shfl_xor_sync(kFull, c, o);
+                }
+                if (g == 0) {
+                    atomicAdd(red + oB1 + 8 * j + 2 * t + q, a);
+                    atomicAdd(red + oB2 + 8 * j + 2 * t + q, b);
+                    atomicAdd(red + oW3 + 8 * j + 2 * t + q, c);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) db3p += __shfl_xor_sync(kFull, db3p, o);
+        if (lane == 0) atomicAdd(red + oB3, db3p);
+        __syncthreads();
+        for (int i = tid; i < SmemPlan::kDecGradFloats; i += blockDim.x) {
+            const float v = red[i];
+            if (v == 0.f) continue;
+            float* dst;
+            if (i < oB1) dst = P.dec.gw1 + i;
+            else if (i < oW2) dst = P.dec.gb1 ? P.dec.gb1 + (i - oB1) : nullptr;
+            else if (i < oB2) dst = P.dec.gw2 + (i - oW2);
+            else if (i < oW3) dst = P.dec.gb2 ? P.dec.gb2 + (i - oB2) : nullptr;
+            else if (i < oB3) dst = P.dec.gw3 + (i - oW3);
+            else dst = P.dec.gb3;
+            if (dst) atomicAdd(dst, v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// dense Adam over several tensors (utils/tools.py:78-79)
+// ------------------------------------------------------------------------------------------------------
+
+struct AdamParams {
+    shine_adam_tensor t[SHINE_ADAM_MAX_TENSORS];
+    int32_t count;
+    float beta1, beta2, omb1, omb2, eps, bc1, bc2_sqrt;
+    int32_t zero_grad;
+};
+
+__global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamParams A) {
+    const shine_adam_tensor& T = A.t[blockIdx.y];
+    const int64_t n4 = T.numel >> 2;
+    const float step_size = T.lr / A.bc1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 p = reinterpret_cast<float4*>(T.param)[i];
+        float4 gr = reinterpret_cast<float4*>(T.grad)[i];
+        float4 m = reinterpret_cast<float4*>(T.exp_avg)[i];
+        float4 v = reinterpret_cast<float4*>(T.exp_avg_sq)[i];
+        float* pp = &p.x; float* gg = &gr.x; float* mm = &m.x; float* vv = &v.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float gk = gg[k];
+            if (T.weight_decay != 0.f) gk = fmaf(T.weight_decay, pp[k], gk);
+            mm[k] = mm[k] + (gk - mm[k]) * A.omb1;                          // torch lerp_
+            vv[k] = A.beta2 * vv[k] + A.omb2 * gk * gk;
+            const float denom = sqrtf(vv[k]) / A.bc2_sqrt + A.eps;
+            pp[k] -= step_size * (mm[k] / denom);
+        }
+        reinterpret_cast<float4*>(T.param)[i] = p;
+        reinterpret_cast<float4*>(T.exp_avg)[i] = m;
+        reinterpret_cast<float4*>(T.exp_avg_sq)[i] = v;
+        if (A.zero_grad) reinterpret_cast<float4*>(T.grad)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // tail (numel % 4) handled by the first block
+    if (blockIdx.x == 0) {
+        for (int64_t i = (n4 << 2) + threadIdx.x; i < T.numel; i += blockDim.x) {
+            float gk = T.grad[i];
+            if (T.weight_decay != 0.f) gk = fmaf(T.weight_decay, T.param[i], gk);
+            const float m = T.exp_avg[i] + (gk - T.exp_avg[i]) * A.omb1;
+            const float v = A.beta2 * T.exp_avg_sq[i] + A.omb2 * gk * gk;
+            T.exp_avg[i] = m; T.exp_avg_sq[i] = v;
+            T.param[i] -= step_size * (m / (sqrtf(v) / A.bc2_sqrt + A.eps));
+            if (A.zero_grad) T.grad[i] = 0.f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+
+inline bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
+
+int check_octree(const shine_octree* o, bool need_grads) {
+    if (!o) return SHINE_ERR_INVALID_ARG;
+    if (o->num_levels < 1 || o->num_levels > SHINE_MAX_LEVELS) return SHINE_ERR_INVALID_ARG;
+    if (o->feature_dim < 4 || (o->feature_dim & 3)) return SHINE_ERR_UNSUPPORTED;
+    for (int i = 0; i < o->num_levels; ++i) {
+        const shine_level& lv = o->lv[i];
+        if (!lv.hash_slots || !lv.features || !is_pow2(lv.hash_capacity) || lv.rows < 1) return SHINE_ERR_INVALID_ARG;
+        if (lv.level < 1 || lv.level > 16) return SHINE_ERR_INVALID_ARG;
+        if (need_grads && !lv.feature_grads) return SHINE_ERR_INVALID_ARG;
+    }
+    return SHINE_OK;
+}
+
+int check_decoder(const shine_decoder* d, const shine_octree* o) {
+    if (!d) return SHINE_ERR_INVALID_ARG;
+    if (d->in_dim != kF || d->hidden != kH || d->mlp_level != 2 || o->feature_dim != kF) return SHINE_ERR_UNSUPPORTED;
+    if (!d->w1 || !d->w2 || !d->w3) return SHINE_ERR_INVALID_ARG;
+    return SHINE_OK;
+}
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+template <int NTF, bool TRAIN, bool DEC_GRAD, int LMAX>
+int launch_fused_t(const StepParams& P, cudaStream_t st) {
+    auto kern = sdf_fused_kernel<NTF, TRAIN, DEC_GRAD, LMAX>;
+    const int smem_floats = SmemPlan::STAGE + (DEC_GRAD ? 8 * SmemPlan::kStagePerWarp : 0);
+    const size_t smem_bytes = (size_t)smem_floats * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return (int)e;
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem_bytes);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    const int blocks_needed = (P.num_tiles + 7) / 8;
+    int grid = sm_count() * per_sm;
+    if (grid > blocks_needed) grid = blocks_needed;
+    if (grid < 1) grid = 1;
+    kern<<<grid, 256, smem_bytes, st>>>(P);
+    return (int)cudaGetLastError();
+}
+
+template <bool TRAIN, bool DEC_GRAD>
+int launch_fused(const StepParams& P, uint32_t flags, cudaStream_t st) {
+    const bool x1 = (flags & SHINE_FLAG_TF32X1) != 0;
+    const bool small = P.oct.num_levels <= 4;
+    if (x1) return small ? launch_fused_t<1, TRAIN, DEC_GRAD, 4>(P, st) : launch_fused_t<1, TRAIN, DEC_GRAD, 8>(P, st);
+    return small ? launch_fused_t<3, TRAIN, DEC_GRAD, 4>(P, st) : launch_fused_t<3, TRAIN, DEC_GRAD, 8>(P, st);
+}
+
+int fill_params(StepParams& P, const shine_octree* oct, const shine_decoder* dec, const float* coord, int64_t n) {
+    if (!coord || n < 0) return SHINE_ERR_INVALID_ARG;
+    if (n > (int64_t)INT32_MAX * 8) return SHINE_ERR_UNSUPPORTED;
+    P.oct = *oct; P.dec = *dec; P.coord = coord; P.n = n;
+    P.num_tiles = (int32_t)((n + kTile - 1) / kTile);
+    P.label = nullptr; P.weight = nullptr; P.d_loss = nullptr; P.pred = nullptr; P.loss = nullptr; P.mask = nullptr;
+    P.mask_level = 0; P.sigma = 1.f; P.loss_scale = 1.f; P.weighted = 0;
+    return SHINE_OK;
+}
+
+template <int LP>
+int launch_query(bool bwd, const shine_octree* oct, const float* coord, int64_t n, float* fwd_out, const float* dfeat,
+                 cudaStream_t st) {
+    const int64_t threads = n * LP;
+    const int64_t blocks = (threads + 255) / 256;
+    if (blocks > INT32_MAX) return SHINE_ERR_UNSUPPORTED;
+    if (bwd) query_bwd_kernel<LP><<<(unsigned)blocks, 256, 0, st>>>(*oct, coord, n, dfeat);
+    else query_fwd_kernel<LP><<<(unsigned)blocks, 256, 0, st>>>(*oct, coord, n, fwd_out);
+    return (int)cudaGetLastError();
+}
+
+int dispatch_query(bool bwd, const shine_octree* oct, const float* coord, int64_t n, float* fwd_out, const float* dfeat,
+                   cudaStream_t st) {
+    switch (oct->feature_dim) {
+        case 4: return launch_query<1>(bwd, oct, coord, n, fwd_out, dfeat, st);
+        case 8: return launch_query<2>(bwd, oct, coord, n, fwd_out, dfeat, st);
+        case 16: return launch_query<4>(bwd, oct, coord, n, fwd_out, dfeat, st);
+        case 32: return launch_query<8>(bwd, oct, coord, n, fwd_out, dfeat, st);
+        default: return SHINE_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------
+
+extern "C" {
+
+int shine_abi_version(void) { return SHINE_ABI_VERSION; }
+
+const char* shine_error_string(int code) {
+    if (code == SHINE_OK) return "ok";
+    if (code == SHINE_ERR_INVALID_ARG) return "shine_b200: invalid argument";
+    if (code == SHINE_ERR_UNSUPPORTED) return "shine_b200: unsupported configuration for the sm_100a kernels";
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "shine_b200: unknown error";
+}
+
+int shine_hash_insert(void* slots, uint32_t capacity, const int64_t* keys, const int32_t* corner_ids, int64_t n,
+                      int32_t node_base, void* stream) {
+    if (!slots || !is_pow2(capacity) || n < 0 || (n > 0 && (!keys || !corner_ids))) return SHINE_ERR_INVALID_ARG;
+    if (n == 0) return SHINE_OK;
+    const int64_t blocks = (n + 255) / 256;
+    hash_insert_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<HashSlot*>(slots),
+                                                                          capacity - 1, keys, corner_ids, n, node_base);
+    return (int)cudaGetLastError();
+}
+
+int shine_points_to_morton(const float* coord, int64_t n, int32_t level, int64_t* morton, void* stream) {
+    if (n < 0 || level < 1 || level > 16 || (n > 0 && (!coord || !morton))) return SHINE_ERR_INVALID_ARG;
+    if (n == 0) return SHINE_OK;
+    points_to_morton_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(coord, n, level, morton);
+    return (int)cudaGetLastError();
+}
+
+int shine_get_indices(const shine_octree* oct, const float* coord, int64_t n, int64_t* out_idx, void* stream) {
+    int rc = check_octree(oct, false);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!coord || !out_idx))) return SHINE_ERR_INVALID_ARG;
+    if (n == 0) return SHINE_OK;
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)oct->num_levels);
+    get_indices_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*oct, coord, n, out_idx);
+    return (int)cudaGetLastError();
+}
+
+int shine_query_fwd(const shine_octree* oct, const float* coord, int64_t n, float* out_feat, void* stream) {
+    int rc = check_octree(oct, false);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!coord || !out_feat))) return SHINE_ERR_INVALID_ARG;
+    if (n == 0) return SHINE_OK;
+    return dispatch_query(false, oct, coord, n, out_feat, nullptr, (cudaStream_t)stream);
+}
+
+int shine_query_bwd(const shine_octree* oct, const float* coord, int64_t n, const float* dfeat, void* stream) {
+    int rc = check_octree(oct, true);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!coord || !dfeat))) return SHINE_ERR_INVALID_ARG;
+    if (n == 0) return SHINE_OK;
+    return dispatch_query(true, oct, coord, n, nullptr, dfeat, (cudaStream_t)stream);
+}
+
+int shine_sdf_infer(const shine_octree* oct, const shine_decoder* dec, const float* coord, int64_t n, float* out_pred,
+                    uint8_t* out_mask, int32_t mask_level, uint32_t flags, void* stream) {
+    int rc = check_octree(oct, false);
+    if (rc) return rc;
+    rc = check_decoder(dec, oct);
+    if (rc) return rc;
+    if (n > 0 && !out_pred) return SHINE_ERR_INVALID_ARG;
+    if (out_mask && (mask_level < 0 || mask_level >= oct->num_levels)) return SHINE_ERR_INVALID_ARG;
+    StepParams P;
+    rc = fill_params(P, oct, dec, coord, n);
+    if (rc) return rc;
+    if (n == 0) return SHINE_OK;
+    P.pred = out_pred; P.mask = out_mask; P.mask_level = mask_level;
+    return launch_fused<false, false>(P, flags, (cudaStream_t)stream);
+}
+
+int shine_sdf_bce_fwd(const shine_octree* oct, const shine_decoder* dec, const float* coord, const float* label,
+                      const float* weight, int64_t n, float sigma, float loss_scale, float* out_pred, float* out_loss,
+                      uint32_t flags, void* stream) {
+    int rc = check_octree(oct, false);
+    if (rc) return rc;
+    rc = check_decoder(dec, oct);
+    if (rc) return rc;
+    if (n > 0 && !label) return SHINE_ERR_INVALID_ARG;
+    if ((flags & SHINE_FLAG_WEIGHTED) && !weight) return SHINE_ERR_INVALID_ARG;
+    if (!(sigma > 0.f)) return SHINE_ERR_INVALID_ARG;
+    StepParams P;
+    rc = fill_params(P, oct, dec, coord, n);
+    if (rc) return rc;
+    if (n == 0) return SHINE_OK;
+    P.label = label; P.weight = weight; P.weighted = (flags & SHINE_FLAG_WEIGHTED) ? 1 : 0;
+    P.sigma = sigma; P.loss_scale = loss_scale; P.pred = out_pred; P.loss = out_loss;
+    return launch_fused<false, false>(P, flags, (cudaStream_t)stream);
+}
+
+int shine_sdf_bce_step(const shine_octree* oct, const shine_decoder* dec, const float* coord, const float* label,
+                       const float* weight, int64_t n, float sigma, float loss_scale, const float* d_loss,
+                       float* out_pred, float* out_loss, uint32_t flags, void* stream) {
+    int rc = check_octree(oct, true);
+    if (rc) return rc;
+    rc = check_decoder(dec, oct);
+    if (rc) return rc;
+    if (n > 0 && !label) return SHINE_ERR_INVALID_ARG;
+    if ((flags & SHINE_FLAG_WEIGHTED) && !weight) return SHINE_ERR_INVALID_ARG;
+    if (!(sigma > 0.f)) return SHINE_ERR_INVALID_ARG;
+    const bool dec_grad = dec->gw1 || dec->gw2 || dec->gw3;
+    if (dec_grad && !(dec->gw1 && dec->gw2 && dec->gw3)) return SHINE_ERR_INVALID_ARG;
+    StepParams P;
+    rc = fill_params(P, oct, dec, coord, n);
+    if (rc) return rc;
+    if (n == 0) return SHINE_OK;
+    P.label = label; P.weight = weight; P.weighted = (flags & SHINE_FLAG_WEIGHTED) ? 1 : 0;
+    P.sigma = sigma; P.loss_scale = loss_scale; P.d_loss = d_loss; P.pred = out_pred; P.loss = out_loss;
+    return dec_grad ? launch_fused<true, true>(P, flags, (cudaStream_t)stream)
+                    : launch_fused<true, false>(P, flags, (cudaStream_t)stream);
+}
+
+int shine_adam_step(const shine_adam_tensor* tensors, int32_t count, float beta1, float beta2, float eps, int32_t step,
+                    int32_t zero_grad, void* stream) {
+    if (!tensors || count < 1 || count > SHINE_ADAM_MAX_TENSORS || step < 1) return SHINE_ERR_INVALID_ARG;
+    AdamParams A;
+    int64_t max_n = 0;
+    for (int i = 0; i < count; ++i) {
+        const shine_adam_tensor& t = tensors[i];
+        if (!t.param || !t.grad || !t.exp_avg || !t.exp_avg_sq || t.numel < 0) return SHINE_ERR_INVALID_ARG;
+        if ((((uintptr_t)t.param | (uintptr_t)t.grad | (uintptr_t)t.exp_avg | (uintptr_t)t.exp_avg_sq) & 15) != 0)
+            return SHINE_ERR_INVALID_ARG;
+        A.t[i] = t;
+        if (t.numel > max_n) max_n = t.numel;
+    }
+    A.count = count; A.beta1 = beta1; A.beta2 = beta2; A.eps = eps; A.zero_grad = zero_grad;
+    A.omb1 = (float)(1.0 - (double)beta1); A.omb2 = (float)(1.0 - (double)beta2);
+    A.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    A.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+    int64_t blocks = (max_n / 4 + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    dim3 grid((unsigned)blocks, (unsigned)count);
+    adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,442 @@
+"""`FeatureOctree` — drop-in for reference model/feature_octree.py:29-298 whose queries run as sm_100a kernels.
+
+Same constructor, attributes and methods as the reference class.  What changes underneath:
+
+* the per-level Python dicts `nodes_lookup_tables[level]` (Morton -> 8 corner rows) become device hash tables
+  of 64-byte slots probed inside the kernels (`csrc/shine_b200.cu`); the dict views are still available
+  (built lazily from the authoritative arrays) for callers that read them;
+* `update()` (reference :114-166) is vectorised torch code instead of Python dict loops but reproduces the
+  reference's row numbering exactly (lexicographic `torch.unique(dim=0)` order, append-only) and draws the
+  new features with the same `randn` calls, so tables match the reference under the same seed/device;
+* `get_indices`, `query_feature` (+ its autograd backward) call the C ABI; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _abi
+from .config import SHINEConfig
+
+# --------------------------------------------------------------------------------------------------------
+# integer helpers (host logic of update(); the kernels carry their own device versions)
+# --------------------------------------------------------------------------------------------------------
+
+
+def quantize_points(x: torch.Tensor, level: int) -> torch.Tensor:
+    """floor(clamp(2^level (x+1)/2, 0, 2^level-1)) in fp32 -> int64 xyz (kaolin quantize_points semantics,
+    reference call site model/feature_octree.py:203)."""
+    res = float(2 ** level)
+    return torch.floor(torch.clamp(res * (x.float() + 1.0) / 2.0, 0, res - 1.0)).long()
+
+
+def _spread3(v: torch.Tensor) -> torch.Tensor:
+    v = v & 0xFFFF
+    v = (v | (v << 16)) & 0x0000FF0000FF
+    v = (v | (v << 8)) & 0x00F00F00F00F
+    v = (v | (v << 4)) & 0x0C30C30C30C3
+    v = (v | (v << 2)) & 0x249249249249
+    return v
+
+
+def _compact3(v: torch.Tensor) -> torch.Tensor:
+    v = v & 0x249249249249
+    v = (v | (v >> 2)) & 0x0C30C30C30C3
+    v = (v | (v >> 4)) & 0x00F00F00F00F
+    v = (v | (v >> 8)) & 0x0000FF0000FF
+    v = (v | (v >> 16)) & 0xFFFF
+    return v
+
+
+def points_to_morton(p: torch.Tensor) -> torch.Tensor:
+    """x -> bit 3i+2, y -> 3i+1, z -> 3i (kaolin points_to_morton, call site model/feature_octree.py:204)."""
+    p = p.long()
+    return (_spread3(p[..., 0]) << 2) | (_spread3(p[..., 1]) << 1) | _spread3(p[..., 2])
+
+
+def morton_to_points(m: torch.Tensor) -> torch.Tensor:
+    m = m.long()
+    return torch.stack((_compact3(m >> 2), _compact3(m >> 1), _compact3(m)), dim=-1)
+
+
+_CORNER_OFFSETS = [[(i >> 2) & 1, (i >> 1) & 1, i & 1] for i in range(8)]
+
+
+def points_to_corners(p: torch.Tensor) -> torch.Tensor:
+    """corner i = p + ((i>>2)&1, (i>>1)&1, i&1): the order pinned by model/feature_octree.py:186-195."""
+    off = torch.tensor(_CORNER_OFFSETS, dtype=p.dtype, device=p.device)
+    return p.unsqueeze(-2) + off
+
+
+def _lex_key(c: torch.Tensor) -> torch.Tensor:
+    """Order-preserving key of lexicographic (x, y, z) — the order of torch.unique(dim=0) (reference :132)."""
+    c = c.long()
+    return (c[..., 0] << 34) | (c[..., 1] << 17) | c[..., 2]
+
+
+def _next_pow2(n: int) -> int:
+    return 1 << max(4, (int(n) - 1).bit_length())
+
+
+class _LevelState:
+    """Authoritative per-level arrays (world level numbering)."""
+
+    def __init__(self, device):
+        self.node_keys = torch.empty(0, dtype=torch.int64, device=device)        # insertion order
+        self.node_ids = torch.empty(0, 8, dtype=torch.int32, device=device)      # rows of the 8 corners
+        self.node_keys_sorted = torch.empty(0, dtype=torch.int64, device=device)
+        self.corner_lex_sorted = torch.empty(0, dtype=torch.int64, device=device)
+        self.corner_rows_sorted = torch.empty(0, dtype=torch.int64, device=device)
+        self.corner_morton_by_row = torch.empty(0, dtype=torch.int64, device=device)
+        self.hash = None          # uint8 [capacity * 64] device tensor
+        self.hash_capacity = 0
+        self.hash_count = 0       # nodes already inserted
+
+
+# --------------------------------------------------------------------------------------------------------
+# autograd bridge for query_feature
+# --------------------------------------------------------------------------------------------------------
+
+
+class _QueryFeature(torch.autograd.Function):
+    """query_feature forward = shine_query_fwd, backward = shine_query_bwd (dense grads like the reference's
+    index_put_(accumulate=True), but scatter-added with vector atomics and misses skipped)."""
+
+    @staticmethod
+    def forward(ctx, octree, coord, *tables):
+        n = coord.shape[0]
+        out = torch.empty(n, octree.feature_dim, dtype=torch.float32, device=coord.device)
+        desc = octree._descriptor(tables, None)
+        _abi.check(_abi.lib().shine_query_fwd(C.byref(desc), _abi.ptr(coord), n, _abi.ptr(out),
+                                              _abi.stream_ptr(coord.device)), "shine_query_fwd")
+        ctx.octree = octree
+        ctx.save_for_backward(coord, *tables)
+        return out
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        coord, *tables = ctx.saved_tensors
+        octree = ctx.octree
+        grads = [torch.zeros_like(t) if need else None
+                 for t, need in zip(tables, ctx.needs_input_grad[2:])]
+        if any(g is not None for g in grads):
+            full = [g if g is not None else torch.zeros_like(t) for g, t in zip(grads, tables)]
+            desc = octree._descriptor(tables, full)
+            dfeat = dfeat.contiguous()
+            _abi.check(_abi.lib().shine_query_bwd(C.byref(desc), _abi.ptr(coord), coord.shape[0], _abi.ptr(dfeat),
+                                                  _abi.stream_ptr(coord.device)), "shine_query_bwd")
+        return (None, None, *grads)
+
+
+# --------------------------------------------------------------------------------------------------------
+# FeatureOctree
+# --------------------------------------------------------------------------------------------------------
+
+
+class FeatureOctree(nn.Module):
+
+    def __init__(self, config: SHINEConfig):
+        super().__init__()
+        # [0 .. max_level]; level 0 is the root (reference :35-44)
+        self.max_level = config.tree_level_world
+        self.leaf_vox_size = config.leaf_vox_size
+        self.featured_level_num = config.tree_level_feat
+        self.free_level_num = self.max_level - self.featured_level_num + 1
+        self.feature_dim = config.feature_dim
+        self.feature_std = config.feature_std
+        self.polynomial_interpolation = config.poly_int_on
+        self.device = config.device
+        if self.featured_level_num < 1:
+            raise ValueError('No level with grid features!')
+        if self.featured_level_num > _abi.MAX_LEVELS:
+            raise ValueError(f'tree_level_feat > {_abi.MAX_LEVELS} is not supported by the sm_100a kernels')
+        self._levels = [_LevelState(self.device) for _ in range(self.max_level + 1)]
+        self._dict_cache = None
+        # coarse -> fine; the last row of each table is the trash-bin (reference :61-63)
+        self.hier_features = nn.ParameterList([])
+        self._last_coord = None
+        self._hier_idx = []
+        # incremental mapping state (reference :70-72)
+        self.importance_weight = []
+        self.features_last_frame = []
+        self.to(config.device)
+
+    # ---- dict views kept for callers that read the reference's tables (reference :46-52) -------------------
+
+    def _build_dicts(self):
+        if self._dict_cache is None:
+            corners, nodes = [], []
+            for st in self._levels:
+                cm = st.corner_morton_by_row.tolist()
+                corners.append(dict(zip(cm, range(len(cm)))))
+                nodes.append(dict(zip(st.node_keys.tolist(), st.node_ids.tolist())))
+            self._dict_cache = (corners, nodes)
+        return self._dict_cache
+
+    @property
+    def corners_lookup_tables(self):
+        return self._build_dicts()[0]
+
+    @property
+    def nodes_lookup_tables(self):
+        return self._build_dicts()[1]
+
+    @property
+    def hierarchical_indices(self):
+        """Bottom-up list of [N,8] int64 for the last queried batch (reference :66-67).  Materialised lazily:
+        the fused kernels never need it, only `Mesher.query_points` / `cal_regularization` read it."""
+        if not self._hier_idx and self._last_coord is not None:
+            self._hier_idx = self._compute_indices(self._last_coord)
+        return self._hier_idx
+
+    @hierarchical_indices.setter
+    def hierarchical_indices(self, value):
+        self._hier_idx = value
+        self._last_coord = None
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_dict_cache"] = None
+        state["_last_coord"] = None
+        state["_hier_idx"] = []
+        levels = []
+        for st in self._levels:  # device hash tables are rebuilt on demand after unpickling
+            cp = _LevelState.__new__(_LevelState)
+            cp.__dict__.update(st.__dict__)
+            cp.hash, cp.hash_capacity, cp.hash_count = None, 0, 0
+            levels.append(cp)
+        state["_levels"] = levels
+        return state
+
+    # ---- reference API -------------------------------------------------------------------------------------
+
+    def set_zero(self):
+        """Re-zero the trash-bin rows (reference :78-81)."""
+        with torch.no_grad():
+            for p in self.hier_features:
+                p[-1].zero_()
+
+    def forward(self, x):
+        return self.query_feature(x)
+
+    def get_morton(self, sample_points, level):
+        points_morton = points_to_morton(quantize_points(sample_points, level))
+        sample_points_with_morton = torch.hstack((sample_points, points_morton.view(-1, 1)))
+        return sample_points_with_morton, set(points_morton.cpu().numpy())
+
+    def get_octree_nodes(self, level):
+        """Node centres at `level` in the [-1,1] cube (reference :94-101)."""
+        nodes = morton_to_points(self._levels[level].node_keys).cpu().numpy()
+        node_size = 2 ** (1 - level)
+        return (nodes * node_size) - 1.0 + 0.5 * node_size
+
+    def is_empty(self):
+        return len(self.hier_features) == 0
+
+    def clear_temp(self):
+        self._hier_idx = []
+        self._last_coord = None
+        self.importance_weight = []
+        self.features_last_frame = []
+
+    @torch.no_grad()
+    def update(self, surface_points, incremental_on=False):
+        """Grow the octree from new surface points (reference :114-166), vectorised.
+
+        Per featured level i: occupied nodes = unique(leaf_morton >> 3(W-i)) in Morton order (what kaolin's
+        unbatched_pointcloud_to_spc yields, reference :116-122); nodes not seen before are new (:124-128); their
+        corners, made unique in lexicographic order (:131-132), get row ids — 0..n-1 for the first frame
+        (:135-137), appended after the existing rows for later frames (:148-151); the trash row is re-appended
+        last (:139-142,153-156); each new node stores its 8 corner rows (:162-166)."""
+        dev = self.device
+        pts = surface_points.to(dev)
+        leaf = torch.unique(points_to_morton(quantize_points(pts, self.max_level)))
+        for i in range(self.max_level + 1):
+            if i < self.free_level_num:
+                continue
+            st = self._levels[i]
+            nodes_m = torch.unique(leaf >> (3 * (self.max_level - i)))
+            if st.node_keys_sorted.numel():
+                pos = torch.searchsorted(st.node_keys_sorted, nodes_m).clamp_(max=st.node_keys_sorted.numel() - 1)
+                is_new = st.node_keys_sorted[pos] != nodes_m
+                new_m = nodes_m[is_new]
+            else:
+                new_m = nodes_m
+            if new_m.numel() == 0:
+                continue
+            corners = points_to_corners(morton_to_points(new_m))            # [n, 8, 3]
+            lex = _lex_key(corners).reshape(-1)
+            lex_unique = torch.unique(lex)                                    # lexicographic (x, y, z)
+            cur = i - self.free_level_num
+            if st.corner_lex_sorted.numel() == 0:   # first frame of this level
+                fresh = lex_unique
+                pre_size = 0
+                fts = self.feature_std * torch.randn(fresh.numel() + 1, self.feature_dim, device=dev)
+                fts[-1] = 0.0
+                self.hier_features.append(nn.Parameter(fts))
+                if incremental_on:
+                    self.importance_weight.append(torch.zeros(fresh.numel() + 1, self.feature_dim, device=dev))
+                    self.features_last_frame.append(fts.clone())
+            else:
+                pos = torch.searchsorted(st.corner_lex_sorted, lex_unique).clamp_(max=st.corner_lex_sorted.numel() - 1)
+                fresh = lex_unique[st.corner_lex_sorted[pos] != lex_unique]
+                pre_size = st.corner_lex_sorted.numel()
+                new_fts = self.feature_std * torch.randn(fresh.numel() + 1, self.feature_dim, device=dev)
+                new_fts[-1] = 0.0
+                self.hier_features[cur] = nn.Parameter(torch.cat((self.hier_features[cur].data[:-1], new_fts), 0))
+                if incremental_on:
+                    new_w = torch.zeros(fresh.numel() + 1, self.feature_dim, device=dev)
+                    self.importance_weight[cur] = torch.cat((self.importance_weight[cur][:-1], new_w), 0)
+                    self.features_last_frame[cur] = self.hier_features[cur].data.clone()
+            if fresh.numel():
+                fresh_rows = pre_size + torch.arange(fresh.numel(), device=dev)
+                all_lex = torch.cat((st.corner_lex_sorted, fresh))
+                all_rows = torch.cat((st.corner_rows_sorted, fresh_rows))
+                order = torch.argsort(all_lex)
+                st.corner_lex_sorted, st.corner_rows_sorted = all_lex[order], all_rows[order]
+                fresh_xyz = torch.stack((fresh >> 34, (fresh >> 17) & 0x1FFFF, fresh & 0x1FFFF), -1)
+                st.corner_morton_by_row = torch.cat((st.corner_morton_by_row, points_to_morton(fresh_xyz)))
+            ids = st.corner_rows_sorted[torch.searchsorted(st.corner_lex_sorted, lex)].reshape(-1, 8).to(torch.int32)
+            st.node_keys = torch.cat((st.node_keys, new_m))
+            st.node_ids = torch.cat((st.node_ids, ids))
+            st.node_keys_sorted = torch.sort(torch.cat((st.node_keys_sorted, new_m))).values
+        self._dict_cache = None
+        self._hier_idx = []
+        self._last_coord = None
+
+    def interpolat(self, x, level, polynomial_on=True):
+        """The 8 blend weights as a tensor (reference :172-196) — kept for API parity; the kernels compute
+        the same expression in registers."""
+        coords = (2 ** level) * (x * 0.5 + 0.5)
+        d = torch.frac(coords)
+        t = 3 * (d ** 2) - 2 * (d ** 3) if polynomial_on else d
+        tx, ty, tz = t[:, 0], t[:, 1], t[:, 2]
+        ux, uy, uz = 1 - tx, 1 - ty, 1 - tz
+        p = torch.stack((ux * uy * uz, ux * uy * tz, ux * ty * uz, ux * ty * tz,
+                         tx * uy * uz, tx * uy * tz, tx * ty * uz, tx * ty * tz), 0)
+        return p.T.unsqueeze(2)
+
+    # ---- device tables -------------------------------------------------------------------------------------
+
+    def _ensure_hash(self):
+        """(Re)build / extend the device hash tables so they hold every node (load factor <= 0.5)."""
+        lib = _abi.lib()
+        for i in range(self.free_level_num, self.max_level + 1):
+            st = self._levels[i]
+            n = st.node_keys.numel()
+            if st.hash is not None and st.hash_count == n:
+                continue
+            _abi.require_cuda(st.node_keys, "FeatureOctree device tables")
+            start = st.hash_count
+            if st.hash is None or 2 * n > st.hash_capacity:
+                st.hash_capacity = _next_pow2(2 * max(n, 1))
+                st.hash = torch.full((st.hash_capacity * _abi.HASH_SLOT_BYTES,), 0xFF, dtype=torch.uint8,
+                                     device=st.node_keys.device)
+                start = 0
+            keys = st.node_keys[start:].contiguous()
+            ids = st.node_ids[start:].contiguous()
+            _abi.check(lib.shine_hash_insert(_abi.ptr(st.hash), st.hash_capacity, _abi.ptr(keys), _abi.ptr(ids),
+                                             n - start, start, _abi.stream_ptr(keys.device)), "shine_hash_insert")
+            st.hash_count = n
+
+    def _descriptor(self, tables=None, grads=None) -> _abi.ShineOctree:
+        """C descriptor, bottom-up like hierarchical_indices (lv[0] = leaf)."""
+        if self.is_empty():
+            raise _abi.ShineB200Error("FeatureOctree is empty: call update() before querying")
+        self._ensure_hash()
+        tables = list(self.hier_features) if tables is None else list(tables)
+        d = _abi.ShineOctree()
+        d.num_levels = self.featured_level_num
+        d.feature_dim = self.feature_dim
+        d.poly_interp = 1 if self.polynomial_interpolation else 0
+        for i in range(self.featured_level_num):
+            level = self.max_level - i
+            k = self.featured_level_num - i - 1
+            st = self._levels[level]
+            t = tables[k]
+            _abi.require_cuda(t, "FeatureOctree.hier_features")
+            if not t.is_contiguous() or t.dtype != torch.float32:
+                raise _abi.ShineB200Error("hier_features must be contiguous fp32")
+            lv = d.lv[i]
+            lv.hash_slots = st.hash.data_ptr()
+            lv.features = t.data_ptr()
+            lv.feature_grads = grads[k].data_ptr() if grads is not None and grads[k] is not None else None
+            lv.hash_capacity = st.hash_capacity
+            lv.rows = t.shape[0]
+            lv.level = level
+        return d
+
+    def _prep_coord(self, coord):
+        _abi.require_cuda(coord, "FeatureOctree query")
+        if coord.dtype != torch.float32 or not coord.is_contiguous():
+            coord = coord.float().contiguous()
+        return coord
+
+    def _compute_indices(self, coord):
+        coord = self._prep_coord(coord.detach())
+        n = coord.shape[0]
+        out = torch.empty(self.featured_level_num, n, 8, dtype=torch.int64, device=coord.device)
+        desc = self._descriptor()
+        _abi.check(_abi.lib().shine_get_indices(C.byref(desc), _abi.ptr(coord), n, _abi.ptr(out),
+                                                _abi.stream_ptr(coord.device)), "shine_get_indices")
+        return list(out.unbind(0))
+
+    def get_indices(self, coord):
+        """Bottom-up list of [N,8] int64 corner rows, -1 x8 where the voxel is not in the tree (reference
+        :199-218) — one GPU hash probe per (point, level) instead of N Python dict.get calls."""
+        self._hier_idx = self._compute_indices(coord)
+        self._last_coord = None
+        return self._hier_idx
+
+    def get_indices_fast(self, coord):
+        """Reference :267-286 dedupes voxels on the host to save dict lookups; on the GPU every probe is O(1),
+        so this is get_indices."""
+        return self.get_indices(coord)
+
+    def query_feature_with_indices(self, coord, hierarchical_indices):
+        """Blend with caller-supplied indices (reference :222-234).  Plain torch gather on the device — kept for
+        API parity (`cal_feature_importance`-style callers); the hot path is `query_feature`."""
+        total = torch.zeros(coord.shape[0], self.feature_dim, device=coord.device)
+        for i in range(self.featured_level_num):
+            level = self.max_level - i
+            k = self.featured_level_num - i - 1
+            w = self.interpolat(coord, level, self.polynomial_interpolation)
+            total = total + (self.hier_features[k][hierarchical_indices[i]] * w).sum(1)
+        return total
+
+    def query_feature(self, coord, faster=False):
+        """All-in-one feature query (reference :237-244): one kernel that hashes the point into each level,
+        gathers the 8 corner rows, blends and sums over levels; autograd scatter-adds into the tables."""
+        if coord.requires_grad:
+            raise NotImplementedError(
+                "d(feature)/d(coord) (eikonal / normal losses, reference utils/tools.py:175-185) is not part of the "
+                "sm_100a hot path yet; run with ekional_loss_on=False")
+        self.set_zero()
+        coord = self._prep_coord(coord)
+        self._last_coord = coord
+        self._hier_idx = []
+        return _QueryFeature.apply(self, coord, *self.hier_features)
+
+    def cal_regularization(self):
+        """Continual-learning regulariser (reference :246-255)."""
+        regularization = 0.
+        idx = self.hierarchical_indices
+        for i in range(self.featured_level_num):
+            k = self.featured_level_num - i - 1
+            unique_indices = idx[i].flatten().unique()
+            difference = self.hier_features[k][unique_indices] - self.features_last_frame[k][unique_indices]
+            regularization += (self.importance_weight[k][unique_indices] * (difference ** 2)).sum()
+        return regularization
+
+    def print_detail(self):
+        print("Current Octomap:")
+        total = 0
+        for level in range(self.featured_level_num):
+            size = self.leaf_vox_size * (2 ** (self.featured_level_num - 1 - level))
+            count = self.hier_features[level].shape[0]
+            print("%.2f m: %d voxel corners" % (size, count))
+            total += count
+        print("memory: %d x %d x 4 = %.3f MB" % (total, self.feature_dim, total * self.feature_dim * 4 / 1024 / 1024))
+        print("--------------------------------")

@@ -1,0 +1,159 @@
+"""`SdfTrainer` — the training-step engine behind the `shine_batch.py`-equivalent loop (reference
+shine_batch.py:105-210) without autograd in the way.
+
+One flat fp32 gradient buffer holds every table level and the decoder (each segment 16-byte aligned), so that
+  * zeroing the gradients is ONE memset (or free: fused into the Adam kernel),
+  * the data-parallel exchange is ONE NCCL all-reduce over NVLink (decoder 1 377 floats + table rows),
+  * `param.grad` of every parameter is a view into it, so stock torch optimizers still work.
+`forward_backward()` = one `shine_sdf_bce_step` launch; `optimizer_step()` = one `shine_adam_step` launch with the
+reference's grouping (utils/tools.py:57-83: Adam betas (0.9, 0.99), eps 1e-15, weight decay on the decoder only,
+per-level lr scaled leaf -> coarse by lr_level_reduce_ratio).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _abi
+from .config import SHINEConfig
+from .decoder import Decoder
+from .feature_octree import FeatureOctree
+
+
+def _align4(n: int) -> int:
+    return (n + 3) & ~3
+
+
+class SdfTrainer:
+    def __init__(self, config: SHINEConfig, octree: FeatureOctree, decoder: Decoder, process_group=None,
+                 tf32x1: bool = False):
+        self.config, self.octree, self.decoder = config, octree, decoder
+        self.group = process_group
+        self.tf32x1 = tf32x1
+        self.lr = config.lr
+        self.step_count = 0
+        self._sig = None
+        self.sigma = config.sigma_sigmoid
+        self._sync()
+
+    # ---- flat buffers --------------------------------------------------------------------------------------
+
+    def _params(self):
+        tables = list(self.octree.hier_features)
+        dec = [p for p in self.decoder.fused_params()]
+        return tables, dec
+
+    def _sync(self):
+        """(Re)bind the flat grad / Adam-state buffers after `octree.update()` replaced the Parameters
+        (reference model/feature_octree.py:156; the reference rebuilds its optimizer too, shine_incre.py:108-109)."""
+        tables, dec = self._params()
+        sig = tuple((p.data_ptr(), tuple(p.shape)) for p in tables + [p for p in dec if p is not None])
+        if sig == self._sig:
+            return
+        dev = tables[0].device
+        _abi.require_cuda(tables[0], "SdfTrainer")
+        sizes = [p.numel() for p in tables] + [p.numel() if p is not None else 0 for p in dec]
+        offs, total = [], 0
+        for s in sizes:
+            offs.append(total)
+            total += _align4(s)
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.step_count = 0   # fresh Adam state, like a rebuilt torch optimizer
+        views = []
+        for p, o, s in zip(tables + dec, offs, sizes):
+            views.append(self.flat_grad[o:o + s].view(p.shape) if p is not None else None)
+        L = len(tables)
+        self.table_grads, self.dec_grads = views[:L], views[L:]
+        self._offs, self._sizes = offs, sizes
+        self._dec_trainable = any(p is not None and p.requires_grad for p in dec)
+        for p, g in zip(tables + dec, views):
+            if p is not None and p.requires_grad:
+                p.grad = g
+        self._sig = sig
+        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    # ---- the hot path --------------------------------------------------------------------------------------
+
+    def forward_backward(self, coord, sdf_label, weight=None, n_norm=None, pred_out=None):
+        """One fused launch: loss value (device scalar, accumulated into self.loss which is zeroed here) and
+        gradients accumulated into the flat buffer.  Caller zeroes grads (zero_grad / fused in optimizer_step)."""
+        self._sync()
+        cfg = self.config
+        n = coord.shape[0]
+        weighted = bool(cfg.loss_weight_on)
+        flags = (_abi.FLAG_REDUCTION_SUM if cfg.loss_reduction == "sum" else 0) | \
+                (_abi.FLAG_WEIGHTED if weighted else 0) | (_abi.FLAG_TF32X1 if self.tf32x1 else 0)
+        scale = 1.0 if cfg.loss_reduction == "sum" else 1.0 / float(n_norm if n_norm else n)
+        od = self.octree._descriptor(None, self.table_grads)
+        dd = self.decoder.c_descriptor(self.dec_grads if self._dec_trainable else None)
+        self.loss.zero_()
+        _abi.check(_abi.lib().shine_sdf_bce_step(
+            C.byref(od), C.byref(dd), _abi.ptr(coord), _abi.ptr(sdf_label),
+            _abi.ptr(weight) if weighted else None, n, float(self.sigma), scale, None,
+            _abi.ptr(pred_out), _abi.ptr(self.loss), flags, _abi.stream_ptr(coord.device)), "shine_sdf_bce_step")
+        return self.loss
+
+    def all_reduce_grads(self):
+        """Data-parallel exchange: ONE collective over the flat buffer (sum; the 1/N_global is already in the
+        per-point gradient scale)."""
+        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                      and torch.distributed.get_world_size() > 1):
+            torch.distributed.all_reduce(self.flat_grad, group=self.group)
+
+    def optimizer_step(self, zero_grad: bool = True):
+        """Dense Adam with the reference's groups (utils/tools.py:57-83) as one multi-tensor launch."""
+        cfg = self.config
+        tables, dec = self._params()
+        self.step_count += 1
+        entries = []
+        L = len(tables)
+
+        def add(p, idx, lr, wd):
+            o, s = self._offs[idx], self._sizes[idx]
+            t = _abi.ShineAdamTensor()
+            t.param, t.grad = p.data_ptr(), self.flat_grad.data_ptr() + 4 * o
+            t.exp_avg, t.exp_avg_sq = self.exp_avg.data_ptr() + 4 * o, self.exp_avg_sq.data_ptr() + 4 * o
+            t.numel, t.lr, t.weight_decay = s, lr, wd
+            entries.append(t)
+
+        for j, p in enumerate(dec):
+            if p is not None and p.requires_grad:
+                add(p, L + j, self.lr, cfg.weight_decay)
+        lr_cur = self.lr
+        for i in range(L):   # leaf first, lr shrinking towards coarse levels (utils/tools.py:68-72)
+            k = L - i - 1
+            if tables[k].requires_grad:
+                add(tables[k], k, lr_cur, 0.0)
+            lr_cur *= cfg.lr_level_reduce_ratio
+        arr = (_abi.ShineAdamTensor * len(entries))(*entries)
+        _abi.check(_abi.lib().shine_adam_step(arr, len(entries), 0.9, 0.99, float(cfg.adam_eps), self.step_count,
+                                              1 if zero_grad else 0, _abi.stream_ptr(tables[0].device)),
+                   "shine_adam_step")
+
+    def train_step(self, coord, sdf_label, weight=None, n_norm=None):
+        """shine_batch.py:123-210: fwd + loss + bwd (+ all-reduce when data parallel) + Adam."""
+        loss = self.forward_backward(coord, sdf_label, weight, n_norm)
+        self.all_reduce_grads()
+        self.optimizer_step(zero_grad=True)
+        return loss
+
+    # ---- host-buffer entry (the reference-facing call with HOST memory) -----------------------------------------
+
+    def step_from_host(self, coord_h, label_h, weight_h=None, optimizer: bool = False) -> float:
+        """coord/label(/weight) are pinned host tensors; copies them in, runs the fused step, reads the loss back."""
+        dev = self.flat_grad.device
+        coord = coord_h.to(dev, non_blocking=True)
+        label = label_h.to(dev, non_blocking=True)
+        weight = weight_h.to(dev, non_blocking=True) if weight_h is not None else None
+        self.zero_grad()
+        loss = self.forward_backward(coord, label, weight)
+        if optimizer:
+            self.all_reduce_grads()
+            self.optimizer_step(zero_grad=False)
+        return float(loss.item())
