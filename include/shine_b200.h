@@ -47,10 +47,14 @@ typedef struct shine_level {
                                  replaces nodes_lookup_tables[level] (dict morton -> 8 corner rows)      */
     const float* features;    /* hier_features[k]: [rows, F] fp32, last row = trash-bin                  */
     float* feature_grads;     /* same shape, accumulated into (+=); may be NULL when no grads are asked  */
+    float* grad_replicas;     /* optional scratch [num_replicas-1, rows, F], all-zero on entry: gradient
+                                 privatisation for small (hot) levels — warps spread their red.adds over the
+                                 replicas to avoid same-address serialisation in L2; fold them back with
+                                 shine_reduce_grad_replicas (which also re-zeroes the scratch)           */
     uint32_t hash_capacity;   /* power of two                                                            */
     int32_t rows;             /* N_l + 1                                                                 */
     int32_t level;            /* octree level in world numbering (leaf = tree_level_world)               */
-    int32_t reserved;
+    int32_t num_replicas;     /* 0/1 = none, else a power of two <= 64                                   */
 } shine_level;
 
 typedef struct shine_octree {
@@ -118,6 +122,10 @@ int shine_sdf_bce_fwd(const shine_octree* oct, const shine_decoder* dec, const f
 int shine_sdf_bce_step(const shine_octree* oct, const shine_decoder* dec, const float* coord,
                        const float* label, const float* weight, int64_t n, float sigma, float loss_scale,
                        const float* d_loss, float* out_pred, float* out_loss, uint32_t flags, void* stream);
+
+/* feature_grads[l] += sum of grad_replicas[l][r]; grad_replicas[l] = 0.  No-op for levels without
+ * replicas.  Part of the backward (the reference's index_put_ is one pass, shine_batch.py:209). */
+int shine_reduce_grad_replicas(const shine_octree* oct, void* stream);
 
 /* Dense Adam (utils/tools.py:78-79: betas (0.9,0.99), eps 1e-15, weight decay as L2 on grads) over up to
  * SHINE_ADAM_MAX_TENSORS tensors in one launch — shine_batch.py:210 `opt.step()`. */

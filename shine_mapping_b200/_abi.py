@@ -11,7 +11,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libshine_b200.so")
+LIB_PATH = os.environ.get("SHINE_B200_LIB") or os.path.join(_HERE, "csrc", "libshine_b200.so")
 
 MAX_LEVELS = 8
 HASH_SLOT_BYTES = 64
@@ -23,7 +23,8 @@ FLAG_TF32X1 = 4
 
 class ShineLevel(C.Structure):
     _fields_ = [("hash_slots", C.c_void_p), ("features", C.c_void_p), ("feature_grads", C.c_void_p),
-                ("hash_capacity", C.c_uint32), ("rows", C.c_int32), ("level", C.c_int32), ("reserved", C.c_int32)]
+                ("grad_replicas", C.c_void_p),
+                ("hash_capacity", C.c_uint32), ("rows", C.c_int32), ("level", C.c_int32), ("num_replicas", C.c_int32)]
 
 
 class ShineOctree(C.Structure):
@@ -58,6 +59,7 @@ SYMBOLS = {
     "shine_sdf_infer": (C.c_int, [_OCT, _DEC, _vp, _i64, _vp, _vp, _i32, _u32, _vp]),
     "shine_sdf_bce_fwd": (C.c_int, [_OCT, _DEC, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _u32, _vp]),
     "shine_sdf_bce_step": (C.c_int, [_OCT, _DEC, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp, _u32, _vp]),
+    "shine_reduce_grad_replicas": (C.c_int, [_OCT, _vp]),
     "shine_adam_step": (C.c_int, [C.POINTER(ShineAdamTensor), _i32, _f32, _f32, _f32, _i32, _i32, _vp]),
 }
 
@@ -86,7 +88,11 @@ def lib() -> C.CDLL:
     return _lib
 
 
+LAUNCHES = {"count": 0}   # successful kernel-launching ABI calls (bench.py reports it as gpu_launches)
+
+
 def check(rc: int, what: str) -> None:
+    LAUNCHES["count"] += 1
     if rc != 0:
         msg = lib().shine_error_string(rc).decode()
         raise ShineB200Error(f"{what} failed: {msg} (code {rc})")

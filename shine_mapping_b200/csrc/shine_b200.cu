@@ -21,6 +21,23 @@
 
 #include "shine_b200.h"
 
+// tuning switches (defaults = the best measured on B200; see profiles/)
+#ifndef SHINE_SPEC_IDS
+#define SHINE_SPEC_IDS 0      // fetch the 8 corner ids speculatively together with the first-probe key
+#endif
+#ifndef SHINE_PARALLEL_PROBE
+#define SHINE_PARALLEL_PROBE 0 // issue every level's first-probe key load before resolving any (costs registers)
+#endif
+#ifndef SHINE_PREFETCH
+#define SHINE_PREFETCH 1      // software-pipeline the next tile's coord/label loads
+#endif
+#ifndef SHINE_TRAIN_MINB
+#define SHINE_TRAIN_MINB 2    // min resident blocks/SM of the training kernel (register cap 65536/(256*MINB))
+#endif
+#ifndef SHINE_INFER_MINB
+#define SHINE_INFER_MINB 4
+#endif
+
 namespace {
 
 // ------------------------------------------------------------------------------------------------------
@@ -107,12 +124,31 @@ __device__ __forceinline__ void red_add_f4(float* p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// gradient privatisation: replica 0 is the caller's grad table, replicas 1.. live in lv.grad_replicas
+__device__ __forceinline__ float* grad_base(const shine_level& lv, uint32_t warp_id, int F) {
+    const uint32_t r = lv.num_replicas > 1 ? (warp_id & (uint32_t)(lv.num_replicas - 1)) : 0u;
+    return r == 0 ? lv.feature_grads : lv.grad_replicas + (size_t)(r - 1) * (size_t)lv.rows * F;
+}
+
 // nodes_lookup_tables[level].get(morton, [-1]*8)  (model/feature_octree.py:205-209) as an open-addressing probe.
 // Returns the slot index or -1.  The first probe loads key speculatively together with the caller's id loads.
 __device__ __forceinline__ int probe_slot(const HashSlot* __restrict__ slots, uint32_t mask, unsigned long long key) {
     uint32_t h = hash_key(key) & mask;
 #pragma unroll 1
     for (uint32_t n = 0; n <= mask; ++n) {
+        const unsigned long long k = __ldg(&slots[h].key);
+        if (k == key) return (int)h;
+        if (k == kEmptyKey) return -1;
+        h = (h + 1) & mask;
+    }
+    return -1;
+}
+
+__device__ __noinline__ int probe_slot_from(const HashSlot* __restrict__ slots, uint32_t mask, unsigned long long key,
+                                            uint32_t start) {
+    uint32_t h = start & mask;
+#pragma unroll 1
+    for (uint32_t n = 0; n < mask; ++n) {
         const unsigned long long k = __ldg(&slots[h].key);
         if (k == key) return (int)h;
         if (k == kEmptyKey) return -1;
@@ -231,10 +267,11 @@ __global__ void __launch_bounds__(256) query_bwd_kernel(const __grid_constant__ 
         const int4 ia = ldg_i4(slots[s].ids), ib = ldg_i4(slots[s].ids + 4);
         const int ids[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
         Blend b; b.init(x, y, z, lv.level, oct.poly_interp != 0);
+        float* gb = grad_base(lv, (uint32_t)(gtid >> 5), F) + 4 * part;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
             const float w = b.w(c);
-            red_add_f4(lv.feature_grads + (int64_t)ids[c] * F + 4 * part, w * d.x, w * d.y, w * d.z, w * d.w);
+            red_add_f4(gb + (int64_t)ids[c] * F, w * d.x, w * d.y, w * d.z, w * d.w);
         }
     }
 }
@@ -260,13 +297,20 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 }
 
 // A operand: fp32 values in A-fragment order, split on demand.  NTF == 3: D += Al*Bh + Ah*Bl + Ah*Bh.
+// activation split for 3xTF32: hi = x with the low 13 mantissa bits cleared (1 LOP), lo = x - hi (exact; the MMA
+// reads its top 19 bits).  x*w = hi*wh + hi*wl + lo*wh + O(2^-20 |x w|): same order as the cvt.rna split, one
+// instruction less per element.
+__device__ __forceinline__ void split_fast(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
 template <int NTF>
 struct AFrag {
     uint32_t hi[4], lo[4];
     __device__ __forceinline__ void set(float a0, float a1, float a2, float a3) {
         if (NTF == 3) {
-            split_tf32(a0, hi[0], lo[0]); split_tf32(a1, hi[1], lo[1]);
-            split_tf32(a2, hi[2], lo[2]); split_tf32(a3, hi[3], lo[3]);
+            split_fast(a0, hi[0], lo[0]); split_fast(a1, hi[1], lo[1]);
+            split_fast(a2, hi[2], lo[2]); split_fast(a3, hi[3], lo[3]);
         } else {
             hi[0] = f2tf32(a0); hi[1] = f2tf32(a1); hi[2] = f2tf32(a2); hi[3] = f2tf32(a3);
         }
@@ -336,7 +380,7 @@ struct SmemPlan {
 };
 
 template <int NTF, bool TRAIN, bool DEC_GRAD, int LMAX>
-__global__ void __launch_bounds__(256) sdf_fused_kernel(const __grid_constant__ StepParams P) {
+__global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MINB) sdf_fused_kernel(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(16) float smem[];
     uint32_t* smu = reinterpret_cast<uint32_t*>(smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -392,37 +436,114 @@ __global__ void __launch_bounds__(256) sdf_fused_kernel(const __grid_constant__ 
     const int warp_global = blockIdx.x * kWarps + warp;
     const int warp_stride = gridDim.x * kWarps;
 
+    // levels are normally consecutive (W, W-1, ...): then floor(2^l u) == floor(2^W u) >> (W - l) bit-exactly, so the
+    // coarser Morton keys are shifts of the leaf key instead of fresh quantise + bit-interleave rounds
+    bool consecutive = true;
+#pragma unroll
+    for (int i = 1; i < LMAX; ++i)
+        if (i < L && P.oct.lv[i].level != P.oct.lv[0].level - i) consecutive = false;
+
+    // software pipeline, depth 1: the next tile's coordinates / label are in flight while this tile computes
+    float nx = 0.f, ny = 0.f, nz = 0.f, nlab = 0.f, nwgt = 1.f;
+    bool nvalid = false;
+    auto prefetch_inputs = [&](int tl) {
+        const int64_t p = (int64_t)tl * kTile + g + 8 * odd;
+        nvalid = tl < P.num_tiles && p < P.n;
+        if (nvalid) {
+            nx = __ldg(P.coord + 3 * p); ny = __ldg(P.coord + 3 * p + 1); nz = __ldg(P.coord + 3 * p + 2);
+            if (P.label) nlab = __ldg(P.label + p);
+            if (P.weighted) nwgt = fabsf(__ldg(P.weight + p));   // shine_batch.py:172 abs()
+        }
+    };
+    prefetch_inputs(warp_global);
+
     for (int tile = warp_global; tile < P.num_tiles; tile += warp_stride) {
         const int64_t base = (int64_t)tile * kTile;
         const int64_t myp = base + g + 8 * odd;
-        const bool valid = myp < P.n;
-        float x = 0.f, y = 0.f, z = 0.f;
-        if (valid) { x = __ldg(P.coord + 3 * myp); y = __ldg(P.coord + 3 * myp + 1); z = __ldg(P.coord + 3 * myp + 2); }
+#if !SHINE_PREFETCH
+        prefetch_inputs(tile);
+#endif
+        const bool valid = nvalid;
+        const float x = nx, y = ny, z = nz, lab = nlab, wgt = nwgt;
+#if SHINE_PREFETCH
+        prefetch_inputs(tile + warp_stride);
+#endif
 
-        // ---- hash walk + gather + blend (model/feature_octree.py:199-234) ----------------------------
+        // ---- hash walk (model/feature_octree.py:199-218): all levels probed in parallel, the 8 corner ids are
+        //      fetched speculatively with the key (same 64-byte slot) so a first-probe hit costs ONE latency ----
         int slot[LMAX];
-        float feat[4] = {0.f, 0.f, 0.f, 0.f};
+#if SHINE_PARALLEL_PROBE
+        int4 ia[LMAX], ib[LMAX];
+        {
+            unsigned long long kq[LMAX], kf[LMAX];
+            const unsigned long long key0 = valid ? morton_of(x, y, z, P.oct.lv[0].level) : 0ull;
 #pragma unroll
-        for (int i = 0; i < LMAX; ++i) {
-            slot[i] = -1;
-            if (i < L && valid) {
-                const shine_level& lv = P.oct.lv[i];
-                const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
-                slot[i] = probe_slot(slots, lv.hash_capacity - 1, morton_of(x, y, z, lv.level));
+            for (int i = 0; i < LMAX; ++i) {
+                slot[i] = -1;
+                if (i < L && valid) {
+                    const shine_level& lv = P.oct.lv[i];
+                    const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
+                    kq[i] = consecutive ? (key0 >> (3 * i)) : morton_of(x, y, z, lv.level);
+                    const uint32_t h = hash_key(kq[i]) & (lv.hash_capacity - 1);
+                    slot[i] = (int)h;
+                    kf[i] = __ldg(&slots[h].key);
+#if SHINE_SPEC_IDS
+                    ia[i] = ldg_i4(slots[h].ids); ib[i] = ldg_i4(slots[h].ids + 4);
+#endif
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < LMAX; ++i) {
+                if (i < L && valid) {
+                    if (kf[i] != kq[i]) {
+                        if (kf[i] == kEmptyKey) {
+                            slot[i] = -1;
+                        } else {   // collision on the first probe (rare at load factor <= 0.5): walk on
+                            const shine_level& lv = P.oct.lv[i];
+                            const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
+                            slot[i] = probe_slot_from(slots, lv.hash_capacity - 1, kq[i], (uint32_t)slot[i] + 1);
+#if SHINE_SPEC_IDS
+                            if (slot[i] >= 0) { ia[i] = ldg_i4(slots[slot[i]].ids); ib[i] = ldg_i4(slots[slot[i]].ids + 4); }
+#endif
+                        }
+                    }
+                }
             }
         }
+#else
+        {
+            const unsigned long long key0 = valid ? morton_of(x, y, z, P.oct.lv[0].level) : 0ull;
+#pragma unroll
+            for (int i = 0; i < LMAX; ++i) {
+                slot[i] = -1;
+                if (i < L && valid) {
+                    const shine_level& lv = P.oct.lv[i];
+                    const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
+                    const unsigned long long kq = consecutive ? (key0 >> (3 * i)) : morton_of(x, y, z, lv.level);
+                    slot[i] = probe_slot(slots, lv.hash_capacity - 1, kq);
+                }
+            }
+        }
+#endif
+
+        // ---- 8-corner gather + blend, summed over levels (model/feature_octree.py:222-234) --------------------
+        float feat[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < LMAX; ++i) {
             if (i < L && slot[i] >= 0) {
                 const shine_level& lv = P.oct.lv[i];
-                const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
-                const int4 ia = ldg_i4(slots[slot[i]].ids), ib = ldg_i4(slots[slot[i]].ids + 4);
                 const float* fb = lv.features + 4 * half;
+#if SHINE_PARALLEL_PROBE && SHINE_SPEC_IDS
+                const int4 ja = ia[i], jb = ib[i];
+#else
+                const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
+                const int4 ja = ldg_i4(slots[slot[i]].ids), jb = ldg_i4(slots[slot[i]].ids + 4);
+#endif
                 float4 v[8];
-                v[0] = ldg_f4(fb + (int64_t)ia.x * kF); v[1] = ldg_f4(fb + (int64_t)ia.y * kF);
-                v[2] = ldg_f4(fb + (int64_t)ia.z * kF); v[3] = ldg_f4(fb + (int64_t)ia.w * kF);
-                v[4] = ldg_f4(fb + (int64_t)ib.x * kF); v[5] = ldg_f4(fb + (int64_t)ib.y * kF);
-                v[6] = ldg_f4(fb + (int64_t)ib.z * kF); v[7] = ldg_f4(fb + (int64_t)ib.w * kF);
+                v[0] = ldg_f4(fb + (int64_t)ja.x * kF); v[1] = ldg_f4(fb + (int64_t)ja.y * kF);
+                v[2] = ldg_f4(fb + (int64_t)ja.z * kF); v[3] = ldg_f4(fb + (int64_t)ja.w * kF);
+                v[4] = ldg_f4(fb + (int64_t)jb.x * kF); v[5] = ldg_f4(fb + (int64_t)jb.y * kF);
+                v[6] = ldg_f4(fb + (int64_t)jb.z * kF); v[7] = ldg_f4(fb + (int64_t)jb.w * kF);
                 Blend b; b.init(x, y, z, lv.level, poly);
                 float4 ls = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -500,8 +621,6 @@ __global__ void __launch_bounds__(256) sdf_fused_kernel(const __grid_constant__ 
         // ---- sdf_bce_loss (utils/loss.py:17-24) + dL/dpred ---------------------------------------------
         float dpo = 0.f;
         if (valid) {
-            const float lab = __ldg(P.label + myp);
-            const float wgt = P.weighted ? fabsf(__ldg(P.weight + myp)) : 1.0f;   // shine_batch.py:172 abs()
             const float zt = 1.0f / (1.0f + expf(-__fdiv_rn(lab, P.sigma)));       // sigmoid(label / sigma)
             const float e = expf(-fabsf(pown));
             const float li = fmaxf(pown, 0.f) - pown * zt + log1pf(e);
@@ -578,7 +697,7 @@ __global__ void __launch_bounds__(256) sdf_fused_kernel(const __grid_constant__ 
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
                     const float b0 = stB[(8 * ks + t) * kWS + 8 * nt + g], b1 = stB[(8 * ks + t + 4) * kWS + 8 * nt + g];
-                    split_tf32(b0, bh[nt].x, bl[nt].x); split_tf32(b1, bh[nt].y, bl[nt].y);
+                    split_fast(b0, bh[nt].x, bl[nt].x); split_fast(b1, bh[nt].y, bl[nt].y);
                 }
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
@@ -600,8 +719,8 @@ __global__ void __launch_bounds__(256) sdf_fused_kernel(const __grid_constant__ 
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
                 uint2 bh, bl;
-                split_tf32(stX[(8 * ks + t) * kF + g], bh.x, bl.x);
-                split_tf32(stX[(8 * ks + t + 4) * kF + g], bh.y, bl.y);
+                split_fast(stX[(8 * ks + t) * kF + g], bh.x, bl.x);
+                split_fast(stX[(8 * ks + t + 4) * kF + g], bh.y, bl.y);
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
                     AFrag<NTF> a;
@@ -624,7 +743,7 @@ __global__ void __launch_bounds__(256) sdf_fused_kernel(const __grid_constant__ 
                 const int4 ia = ldg_i4(slots[slot[i]].ids), ib = ldg_i4(slots[slot[i]].ids + 4);
                 const int ids[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
                 Blend b; b.init(x, y, z, lv.level, poly);
-                float* gb = lv.feature_grads + 4 * half;
+                float* gb = grad_base(lv, (uint32_t)tile, kF) + 4 * half;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const float w = b.w(c);
@@ -693,6 +812,28 @@ __global__ void __launch_bounds__(256) sdf_fused_kernel(const __grid_constant__ 
 }
 
 // ------------------------------------------------------------------------------------------------------
+// fold the gradient replicas back: grads[l] += sum_r replicas[l][r]; replicas[l] = 0
+// ------------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) reduce_replicas_kernel(const __grid_constant__ shine_octree oct) {
+    const shine_level& lv = oct.lv[blockIdx.y];
+    if (lv.num_replicas <= 1 || !lv.grad_replicas || !lv.feature_grads) return;
+    const int64_t n4 = (int64_t)lv.rows * oct.feature_dim / 4;
+    float4* main4 = reinterpret_cast<float4*>(lv.feature_grads);
+    float4* rep4 = reinterpret_cast<float4*>(lv.grad_replicas);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 acc = main4[i];
+        for (int r = 0; r < lv.num_replicas - 1; ++r) {
+            const float4 v = rep4[(int64_t)r * n4 + i];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            rep4[(int64_t)r * n4 + i] = zero;
+        }
+        main4[i] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // dense Adam over several tensors (utils/tools.py:78-79)
 // ------------------------------------------------------------------------------------------------------
 
@@ -756,6 +897,8 @@ int check_octree(const shine_octree* o, bool need_grads) {
         if (!lv.hash_slots || !lv.features || !is_pow2(lv.hash_capacity) || lv.rows < 1) return SHINE_ERR_INVALID_ARG;
         if (lv.level < 1 || lv.level > 16) return SHINE_ERR_INVALID_ARG;
         if (need_grads && !lv.feature_grads) return SHINE_ERR_INVALID_ARG;
+        if (lv.num_replicas > 1 && (!is_pow2((uint32_t)lv.num_replicas) || lv.num_replicas > 64 || !lv.grad_replicas))
+            return SHINE_ERR_INVALID_ARG;
     }
     return SHINE_OK;
 }
@@ -784,12 +927,19 @@ int launch_fused_t(const StepParams& P, cudaStream_t st) {
     auto kern = sdf_fused_kernel<NTF, TRAIN, DEC_GRAD, LMAX>;
     const int smem_floats = SmemPlan::STAGE + (DEC_GRAD ? 8 * SmemPlan::kStagePerWarp : 0);
     const size_t smem_bytes = (size_t)smem_floats * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) return (int)e;
-    int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem_bytes);
-    if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1) per_sm = 1;
+    static int per_sm_cached = 0;   // per template instantiation; one process drives one GPU
+    cudaError_t e;
+    if (per_sm_cached == 0) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return (int)e;
+        int q = 1;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, 256, smem_bytes);
+        if (e != cudaSuccess) return (int)e;
+        per_sm_cached = q < 1 ? 1 : q;
+    }
+    const int per_sm = per_sm_cached;
     const int blocks_needed = (P.num_tiles + 7) / 8;
     int grid = sm_count() * per_sm;
     if (grid > blocks_needed) grid = blocks_needed;
@@ -807,7 +957,7 @@ int launch_fused(const StepParams& P, uint32_t flags, cudaStream_t st) {
 }
 
 int fill_params(StepParams& P, const shine_octree* oct, const shine_decoder* dec, const float* coord, int64_t n) {
-    if (!coord || n < 0) return SHINE_ERR_INVALID_ARG;
+    if (n < 0 || (n > 0 && !coord)) return SHINE_ERR_INVALID_ARG;
     if (n > (int64_t)INT32_MAX * 8) return SHINE_ERR_UNSUPPORTED;
     P.oct = *oct; P.dec = *dec; P.coord = coord; P.n = n;
     P.num_tiles = (int32_t)((n + kTile - 1) / kTile);
@@ -954,6 +1104,24 @@ int shine_sdf_bce_step(const shine_octree* oct, const shine_decoder* dec, const 
     P.sigma = sigma; P.loss_scale = loss_scale; P.d_loss = d_loss; P.pred = out_pred; P.loss = out_loss;
     return dec_grad ? launch_fused<true, true>(P, flags, (cudaStream_t)stream)
                     : launch_fused<true, false>(P, flags, (cudaStream_t)stream);
+}
+
+int shine_reduce_grad_replicas(const shine_octree* oct, void* stream) {
+    int rc = check_octree(oct, false);
+    if (rc) return rc;
+    int64_t max_n4 = 0;
+    for (int i = 0; i < oct->num_levels; ++i)
+        if (oct->lv[i].num_replicas > 1 && oct->lv[i].feature_grads) {
+            const int64_t n4 = (int64_t)oct->lv[i].rows * oct->feature_dim / 4;
+            if (n4 > max_n4) max_n4 = n4;
+        }
+    if (max_n4 == 0) return SHINE_OK;
+    int64_t blocks = (max_n4 + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 4;
+    if (blocks > cap) blocks = cap;
+    dim3 grid((unsigned)blocks, (unsigned)oct->num_levels);
+    reduce_replicas_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*oct);
+    return (int)cudaGetLastError();
 }
 
 int shine_adam_step(const shine_adam_tensor* tensors, int32_t count, float beta1, float beta2, float eps, int32_t step,

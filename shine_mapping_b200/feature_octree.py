@@ -13,6 +13,7 @@ Same constructor, attributes and methods as the reference class
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -123,10 +124,11 @@ class _QueryFeature(torch.autograd.Function):
                  for t, need in zip(tables, ctx.needs_input_grad[2:])]
         if any(g is not None for g in grads):
             full = [g if g is not None else torch.zeros_like(t) for g, t in zip(grads, tables)]
-            desc = octree._descriptor(tables, full)
+            desc = octree._descriptor(tables, full, n_points=coord.shape[0])
             dfeat = dfeat.contiguous()
             _abi.check(_abi.lib().shine_query_bwd(C.byref(desc), _abi.ptr(coord), coord.shape[0], _abi.ptr(dfeat),
                                                   _abi.stream_ptr(coord.device)), "shine_query_bwd")
+            octree._reduce_replicas(desc, coord.device)
         return (None, None, *grads)
 
 
@@ -154,6 +156,7 @@ class FeatureOctree(nn.Module):
             raise ValueError(f'tree_level_feat > {_abi.MAX_LEVELS} is not supported by the sm_100a kernels')
         self._levels = [_LevelState(self.device) for _ in range(self.max_level + 1)]
         self._dict_cache = None
+        self._grad_scratch = {}   # k -> zero-invariant replica scratch (gradient privatisation)
         # coarse -> fine; the last row of each table is the trash-bin (reference :61-63)
         self.hier_features = nn.ParameterList([])
         self._last_coord = None
@@ -199,6 +202,7 @@ class FeatureOctree(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_dict_cache"] = None
+        state["_grad_scratch"] = {}
         state["_last_coord"] = None
         state["_hier_idx"] = []
         levels = []
@@ -341,8 +345,33 @@ class FeatureOctree(nn.Module):
                                              n - start, start, _abi.stream_ptr(keys.device)), "shine_hash_insert")
             st.hash_count = n
 
-    def _descriptor(self, tables=None, grads=None) -> _abi.ShineOctree:
-        """C descriptor, bottom-up like hierarchical_indices (lv[0] = leaf)."""
+    # Same-address red.add serialises in L2: a level with few rows that receives many updates per step is
+    # privatised into R replicas (R = pow2, chosen so that a row sees about _REPLICA_TARGET updates per replica).
+    _REPLICA_TARGET = int(os.environ.get("SHINE_REPLICA_TARGET", "256"))
+    _REPLICA_MAX = int(os.environ.get("SHINE_REPLICA_MAX", "32"))
+
+    def _replicas_for(self, k: int, rows: int, n_points: int, device) -> tuple[int, torch.Tensor | None]:
+        want = (8 * n_points) // max(1, rows * self._REPLICA_TARGET)
+        r = 1
+        while r * 2 <= min(want, self._REPLICA_MAX):
+            r *= 2
+        if r <= 1:
+            return 1, None
+        need = (r - 1) * rows * self.feature_dim
+        buf = self._grad_scratch.get(k)
+        if buf is None or buf.numel() < need or buf.device != device:
+            buf = torch.zeros((self._REPLICA_MAX - 1) * rows * self.feature_dim, dtype=torch.float32, device=device)
+            self._grad_scratch[k] = buf
+        return r, buf
+
+    def _reduce_replicas(self, desc, device) -> None:
+        if any(desc.lv[i].num_replicas > 1 for i in range(desc.num_levels)):
+            _abi.check(_abi.lib().shine_reduce_grad_replicas(C.byref(desc), _abi.stream_ptr(device)),
+                       "shine_reduce_grad_replicas")
+
+    def _descriptor(self, tables=None, grads=None, n_points: int = 0) -> _abi.ShineOctree:
+        """C descriptor, bottom-up like hierarchical_indices (lv[0] = leaf).  With grads and n_points, small hot
+        levels get gradient replicas (call _reduce_replicas after the backward kernel)."""
         if self.is_empty():
             raise _abi.ShineB200Error("FeatureOctree is empty: call update() before querying")
         self._ensure_hash()
@@ -366,6 +395,10 @@ class FeatureOctree(nn.Module):
             lv.hash_capacity = st.hash_capacity
             lv.rows = t.shape[0]
             lv.level = level
+            if lv.feature_grads and n_points:
+                r, buf = self._replicas_for(k, t.shape[0], n_points, t.device)
+                if r > 1:
+                    lv.num_replicas, lv.grad_replicas = r, buf.data_ptr()
         return d
 
     def _prep_coord(self, coord):

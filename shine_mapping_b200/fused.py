@@ -57,17 +57,21 @@ class _SdfBce(torch.autograd.Function):
         loss = torch.zeros((), dtype=torch.float32, device=dev)
         need_t = [p.requires_grad for p in tables]
         need_d = [p is not None and p.requires_grad for p in dparams]
-        want_grad = torch.is_grad_enabled() and (any(need_t) or any(need_d))
+        # forward() runs under no_grad; needs_input_grad already folds in the caller's grad mode
+        need_t = [bool(x) for x in ctx.needs_input_grad[11:11 + L]]
+        need_d = [bool(x) for x in ctx.needs_input_grad[11 + L:]]
+        want_grad = any(need_t) or any(need_d)
         ctx.octree, ctx.decoder = octree, decoder
         ctx.cfg = (sigma, scale, flags, n, need_t, need_d)
         if want_grad and single_pass:
             tgrads = [torch.zeros_like(p) for p in tables]
             dgrads = [torch.zeros_like(p) if (p is not None and any(need_d)) else None for p in dparams]
-            od = octree._descriptor(tables, tgrads)
+            od = octree._descriptor(tables, tgrads, n_points=n)
             dd = decoder.c_descriptor(dgrads if any(need_d) else None)
             _abi.check(lib.shine_sdf_bce_step(C.byref(od), C.byref(dd), _abi.ptr(coord), _abi.ptr(label),
                                               _abi.ptr(weight), n, sigma, scale, None, _abi.ptr(pred),
                                               _abi.ptr(loss), flags, stream), "shine_sdf_bce_step")
+            octree._reduce_replicas(od, dev)
             ctx.stash = (tgrads, dgrads)
         else:
             od = octree._descriptor(tables, None)
@@ -97,12 +101,13 @@ class _SdfBce(torch.autograd.Function):
             tables, dparams = params[:L], params[L:]
             tgrads = [torch.zeros_like(p) for p in tables]
             dgrads = [torch.zeros_like(p) if (p is not None and any(need_d)) else None for p in dparams]
-            od = octree._descriptor(tables, tgrads)
+            od = octree._descriptor(tables, tgrads, n_points=n)
             dd = decoder.c_descriptor(dgrads if any(need_d) else None)
             dl = dloss.detach().float().contiguous()
             _abi.check(_abi.lib().shine_sdf_bce_step(
                 C.byref(od), C.byref(dd), _abi.ptr(coord), _abi.ptr(label), _abi.ptr(weight), n, sigma, scale,
                 _abi.ptr(dl), None, None, flags, _abi.stream_ptr(coord.device)), "shine_sdf_bce_step")
+            octree._reduce_replicas(od, coord.device)
         out_t = [g if need else None for g, need in zip(tgrads, need_t)]
         out_d = [g if need else None for g, need in zip(dgrads, need_d)]
         return (None,) * 11 + tuple(out_t) + tuple(out_d)

@@ -118,7 +118,7 @@ class SamplePool:
 
 
 def build_scene_map(config: SHINEConfig, octree, n_azimuth: int, n_frames: int = 1, frame_step_m: float = 1.0,
-                    seed: int = 42, device=None):
+                    seed: int = 42, device=None, origin_x0: float = 0.0):
     """Scan the analytic scene from `n_frames` poses along +x, sample every scan, grow the octree from the
     surface samples (weight > 0; dataset/lidar_dataset.py:212-218) and return the SamplePool."""
     device = device or config.device
@@ -126,9 +126,11 @@ def build_scene_map(config: SHINEConfig, octree, n_azimuth: int, n_frames: int =
     gen.manual_seed(seed)
     dirs = lidar_directions(n_azimuth, device=device)
     boxes = default_boxes(device)
+    boxes[:, 0] += origin_x0
+    boxes[:, 3] += origin_x0
     pool = SamplePool(device)
     for f in range(n_frames):
-        origin = torch.tensor([f * frame_step_m, 0.0, 0.0], device=device)
+        origin = torch.tensor([origin_x0 + f * frame_step_m, 0.0, 0.0], device=device)
         hits = raycast_scene(origin, dirs, boxes, min_range=config.min_range, max_range=config.pc_radius)
         coord, label, weight = sample_rays(hits * config.scale, origin * config.scale, config, gen)
         if config.octree_from_surface_samples:

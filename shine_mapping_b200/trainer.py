@@ -27,8 +27,14 @@ def _align4(n: int) -> int:
 
 class SdfTrainer:
     def __init__(self, config: SHINEConfig, octree: FeatureOctree, decoder: Decoder, process_group=None,
-                 tf32x1: bool = False):
+                 tf32x1: bool = False, shard_mode: str = "replicated"):
+        """shard_mode (multi-GPU, see dist.py): "replicated" = every rank holds the whole table and a slice of the
+        point batch -> all-reduce the whole flat gradient; "spatial" = every rank owns its own octree block and
+        the samples inside it (BASELINE config 5) -> only the decoder segment is all-reduced."""
+        if shard_mode not in ("replicated", "spatial"):
+            raise ValueError(shard_mode)
         self.config, self.octree, self.decoder = config, octree, decoder
+        self.shard_mode = shard_mode
         self.group = process_group
         self.tf32x1 = tf32x1
         self.lr = config.lr
@@ -67,6 +73,7 @@ class SdfTrainer:
             views.append(self.flat_grad[o:o + s].view(p.shape) if p is not None else None)
         L = len(tables)
         self.table_grads, self.dec_grads = views[:L], views[L:]
+        self.dec_flat = self.flat_grad[offs[L]:]          # contiguous decoder segment (1 377 floats + padding)
         self._offs, self._sizes = offs, sizes
         self._dec_trainable = any(p is not None and p.requires_grad for p in dec)
         for p, g in zip(tables + dec, views):
@@ -90,13 +97,14 @@ class SdfTrainer:
         flags = (_abi.FLAG_REDUCTION_SUM if cfg.loss_reduction == "sum" else 0) | \
                 (_abi.FLAG_WEIGHTED if weighted else 0) | (_abi.FLAG_TF32X1 if self.tf32x1 else 0)
         scale = 1.0 if cfg.loss_reduction == "sum" else 1.0 / float(n_norm if n_norm else n)
-        od = self.octree._descriptor(None, self.table_grads)
+        od = self.octree._descriptor(None, self.table_grads, n_points=n)
         dd = self.decoder.c_descriptor(self.dec_grads if self._dec_trainable else None)
         self.loss.zero_()
         _abi.check(_abi.lib().shine_sdf_bce_step(
             C.byref(od), C.byref(dd), _abi.ptr(coord), _abi.ptr(sdf_label),
             _abi.ptr(weight) if weighted else None, n, float(self.sigma), scale, None,
             _abi.ptr(pred_out), _abi.ptr(self.loss), flags, _abi.stream_ptr(coord.device)), "shine_sdf_bce_step")
+        self.octree._reduce_replicas(od, coord.device)
         return self.loss
 
     def all_reduce_grads(self):
@@ -104,7 +112,9 @@ class SdfTrainer:
         per-point gradient scale)."""
         if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
                                       and torch.distributed.get_world_size() > 1):
-            torch.distributed.all_reduce(self.flat_grad, group=self.group)
+            buf = self.dec_flat if self.shard_mode == "spatial" else self.flat_grad
+            if buf.numel() and (self.shard_mode != "spatial" or self._dec_trainable):
+                torch.distributed.all_reduce(buf, group=self.group)
 
     def optimizer_step(self, zero_grad: bool = True):
         """Dense Adam with the reference's groups (utils/tools.py:57-83) as one multi-tensor launch."""

@@ -28,10 +28,11 @@ DEC_KEYS = ["layers.0.weight", "layers.0.bias", "layers.1.weight", "layers.1.bia
 
 def make_config(feat_levels=2, world_level=12, leaf_vox=0.2, device="cpu", **kw):
     from shine_mapping_b200.config import SHINEConfig
-    cfg = SHINEConfig(tree_level_world=world_level, tree_level_feat=feat_levels, leaf_vox_size=leaf_vox,
-                      device=device, surface_sample_range_m=0.3, surface_sample_n=3, free_sample_begin_ratio=0.3,
-                      free_sample_end_dist_m=0.8, free_sample_n=3, min_range=3.0, pc_radius=30.0, **kw)
-    return cfg
+    base = dict(tree_level_world=world_level, tree_level_feat=feat_levels, leaf_vox_size=leaf_vox, device=device,
+                surface_sample_range_m=0.3, surface_sample_n=3, free_sample_begin_ratio=0.3,
+                free_sample_end_dist_m=0.8, free_sample_n=3, min_range=3.0, pc_radius=30.0)
+    base.update(kw)
+    return SHINEConfig(**base)
 
 
 def make_case(n_points=3000, n_batch=2048, feat_levels=2, seed=0, n_frames=1, poly=True, weighted=False,

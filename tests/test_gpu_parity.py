@@ -1,0 +1,218 @@
+"""Parity of the sm_100a path (through the C ABI behind the package classes) against the CPU oracle and the
+reference-minted golden vectors.  Tolerances are stated in tests/parity_utils.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from tests.parity_utils import (DEC_KEYS, GOLDEN_NAMES, build_cuda_models, compare_step, load_golden, make_case,
+                                run_cuda_step, run_oracle_step)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _lib(built_lib):
+    assert torch.cuda.is_available()
+    return built_lib
+
+
+# ---- against the reference's own outputs -----------------------------------------------------------------
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_cuda_matches_reference_golden(name):
+    case, exp = load_golden(name)
+    got = run_cuda_step(case, DEV)
+    if case["cfg"]["decoder_frozen"]:
+        got["dec_grads"] = {}
+    print(name, compare_step(got, exp))
+
+
+# ---- against the oracle on seeded synthetic batches -----------------------------------------------------
+
+@pytest.mark.parametrize("levels,poly,weighted,reduction,frames", [
+    (1, True, False, "mean", 1), (2, True, False, "mean", 1), (3, False, True, "sum", 2),
+    (4, True, False, "mean", 1), (4, True, True, "mean", 2), (4, False, False, "sum", 1),
+])
+def test_fused_step_matches_oracle(levels, poly, weighted, reduction, frames):
+    case = make_case(n_points=2500, n_batch=3000, feat_levels=levels, seed=10 + levels, n_frames=frames,
+                     poly=poly, weighted=weighted, reduction=reduction)
+    print(compare_step(run_cuda_step(case, DEV), run_oracle_step(case)))
+
+
+@pytest.mark.parametrize("n_batch", [0, 1, 15, 16, 17, 255])
+def test_ragged_batch_sizes(n_batch):
+    """Tile tails: 16 stragglers are always appended, so N = n_batch + 16 covers 16..271."""
+    case = make_case(n_points=1500, n_batch=n_batch, feat_levels=2, seed=5)
+    print(compare_step(run_cuda_step(case, DEV), run_oracle_step(case)))
+
+
+def test_two_pass_mode_matches_oracle():
+    case = make_case(n_points=2000, n_batch=2000, feat_levels=3, seed=21)
+    print(compare_step(run_cuda_step(case, DEV, single_pass=False), run_oracle_step(case)))
+
+
+def test_unfused_class_surface_matches_oracle():
+    """query_feature kernel + torch MLP + torch loss (the reference call sequence verbatim)."""
+    case = make_case(n_points=2000, n_batch=2000, feat_levels=4, seed=22)
+    print(compare_step(run_cuda_step(case, DEV, unfused=True), run_oracle_step(case)))
+
+
+def test_plain_tf32_flag_is_close():
+    case = make_case(n_points=2000, n_batch=2000, feat_levels=2, seed=23)
+    got, want = run_cuda_step(case, DEV, tf32x1=True), run_oracle_step(case)
+    print(compare_step(got, want, pred_atol=5e-3, pred_rtol=5e-3, grad_rel=3e-2))
+
+
+def test_frozen_decoder_gives_only_table_grads():
+    from shine_mapping_b200 import sdf_bce_step
+    case = make_case(n_points=2000, n_batch=2000, feat_levels=4, seed=24)
+    cfg, octree, dec = build_cuda_models(case, DEV, freeze_decoder=True)
+    coord = torch.from_numpy(case["coord"]).to(DEV); label = torch.from_numpy(case["label"]).to(DEV)
+    loss = sdf_bce_step(octree, dec, coord, label, case["cfg"]["sigma"])
+    loss.backward()
+    want = run_oracle_step(case)
+    for p, w in zip(octree.hier_features, want["table_grads"]):
+        g = p.grad.cpu().numpy()[:-1]
+        assert np.abs(g - w[:-1]).max() <= 2e-4 * np.abs(w).max() + 1e-10
+    assert all(p.grad is None for p in dec.parameters())
+
+
+def test_empty_batch_is_ok():
+    from shine_mapping_b200 import sdf_infer
+    case = make_case(n_points=1500, n_batch=0, feat_levels=2, seed=5)
+    cfg, octree, dec = build_cuda_models(case, DEV)
+    empty = torch.empty(0, 3, device=DEV)
+    assert octree.query_feature(empty).shape == (0, 8)
+    assert [t.shape for t in octree.get_indices(empty)] == [(0, 8)] * 2
+    assert sdf_infer(octree, dec, empty).shape == (0,)
+
+
+def test_infer_and_mask_match_step_pred():
+    from shine_mapping_b200 import sdf_infer
+    case = make_case(n_points=2500, n_batch=3000, feat_levels=3, seed=31)
+    cfg, octree, dec = build_cuda_models(case, DEV)
+    coord = torch.from_numpy(case["coord"]).to(DEV)
+    want = run_oracle_step(case)
+    for lvl in range(3):
+        pred, mask = sdf_infer(octree, dec, coord, mask_level=lvl)
+        assert np.abs(pred.cpu().numpy() - want["pred"]).max() < 2e-5
+        assert np.array_equal(mask.cpu().numpy(), (want["indices"][lvl] >= 0).all(1))
+
+
+def test_points_to_morton_bit_exact():
+    from shine_mapping_b200 import _abi
+    from oracle import shine_oracle as orc
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand(200000, 3, generator=g) * 2.4 - 1.2)
+    x[:8] = torch.tensor([[-1, -1, -1], [1, 1, 1], [0, 0, 0], [1 - 2 ** -12, 2 ** -12, -2 ** -12], [0.5, -0.5, 0.25],
+                          [-1.0000001, 0.99999994, 0.9999999], [3, -3, 0], [2 ** -11, 2 ** -10, 2 ** -9]])
+    xd = x.to(DEV).contiguous()
+    for level in (1, 5, 9, 12, 15):
+        out = torch.empty(x.shape[0], dtype=torch.int64, device=DEV)
+        _abi.check(_abi.lib().shine_points_to_morton(_abi.ptr(xd), x.shape[0], level, _abi.ptr(out),
+                                                     _abi.stream_ptr()), "morton")
+        want = orc.points_to_morton(orc.quantize_points(x.numpy(), level))
+        assert np.array_equal(out.cpu().numpy(), want), level
+
+
+# ---- size-independent properties at BASELINE scale ------------------------------------------------------
+
+def test_large_batch_properties():
+    """1M points, L=4: (a) interpolation weights sum to 1 => per level, the column sums of the table gradient
+    equal the column sums of dL/dfeature over the points that hit that level; (b) two runs give identical
+    indices and (up to atomic ordering) identical gradients; (c) pred of the step == pred of the inference
+    kernel bit-for-bit."""
+    from shine_mapping_b200 import SdfTrainer, sdf_infer, synth
+    from tests.parity_utils import make_config
+    from shine_mapping_b200 import Decoder, FeatureOctree
+    torch.manual_seed(1)
+    cfg = make_config(4, device=DEV, pc_radius=50.0)
+    octree, dec = FeatureOctree(cfg), Decoder(cfg)
+    pool = synth.build_scene_map(cfg, octree, n_azimuth=512, n_frames=2, seed=1, device=DEV)
+    n = 1 << 20
+    coord, label, weight = pool.get_batch(n)
+    tr = SdfTrainer(cfg, octree, dec)
+    pred = torch.empty(n, device=DEV)
+    tr.zero_grad(); tr.forward_backward(coord, label, weight, pred_out=pred)
+    g1 = tr.flat_grad.clone()
+    tr.zero_grad(); tr.forward_backward(coord, label, weight)
+    g2 = tr.flat_grad.clone()
+    assert (g1 - g2).abs().max() <= 1e-4 * g1.abs().max()
+    assert torch.equal(pred, sdf_infer(octree, dec, coord))
+    # (a) with the unfused autograd path giving dL/dfeature
+    feat = octree.query_feature(coord).detach().requires_grad_(True)
+    loss = torch.nn.functional.binary_cross_entropy_with_logits(
+        dec.sdf(feat), torch.sigmoid(label / cfg.sigma_sigmoid))
+    loss.backward()
+    idx = octree.get_indices(coord)
+    for i in range(4):
+        hit = (idx[i] >= 0).all(1)
+        want = feat.grad[hit].double().sum(0)
+        got = tr.table_grads[4 - i - 1].double().sum(0)
+        assert torch.allclose(got, want, rtol=2e-3, atol=1e-7), (i, got, want)
+    # loss value agrees with the torch composition
+    assert abs(float(tr.loss) - float(loss)) <= 2e-5 * abs(float(loss))
+
+
+# ---- optimizer + trainer ---------------------------------------------------------------------------------
+
+def test_adam_kernel_matches_torch_adam():
+    from shine_mapping_b200 import SdfTrainer
+    case = make_case(n_points=2000, n_batch=4096, feat_levels=3, seed=41)
+    cfg, octree, dec = build_cuda_models(case, DEV)
+    cfg.lr, cfg.weight_decay, cfg.lr_level_reduce_ratio = 0.01, 1e-7, 0.7
+    cfg2, octree2, dec2 = build_cuda_models(case, DEV)
+    coord = torch.from_numpy(case["coord"]).to(DEV); label = torch.from_numpy(case["label"]).to(DEV)
+    tr = SdfTrainer(cfg, octree, dec)
+    # torch reference optimiser with the reference grouping (utils/tools.py:57-83)
+    groups = [{"params": list(dec2.fused_params()), "lr": cfg.lr, "weight_decay": cfg.weight_decay}]
+    lr = cfg.lr
+    feats = list(octree2.parameters())
+    for i in range(3):
+        groups.append({"params": feats[3 - i - 1], "lr": lr}); lr *= cfg.lr_level_reduce_ratio
+    opt = torch.optim.Adam(groups, betas=(0.9, 0.99), eps=cfg.adam_eps)
+    from shine_mapping_b200 import sdf_bce_step
+    for it in range(5):
+        tr.zero_grad() if it == 0 else None
+        tr.train_step(coord, label)
+        opt.zero_grad(set_to_none=True)
+        sdf_bce_step(octree2, dec2, coord, label, cfg.sigma_sigmoid).backward()
+        opt.step()
+    for a, b in zip(octree.hier_features, octree2.hier_features):
+        assert torch.allclose(a[:-1], b[:-1], rtol=2e-3, atol=2e-5), (a[:-1] - b[:-1]).abs().max()
+    for a, b in zip(dec.fused_params(), dec2.fused_params()):
+        assert torch.allclose(a, b, rtol=2e-3, atol=2e-5)
+
+
+def test_training_reduces_loss():
+    from shine_mapping_b200 import SdfTrainer
+    case = make_case(n_points=3000, n_batch=8192, feat_levels=4, seed=42)
+    cfg, octree, dec = build_cuda_models(case, DEV)
+    cfg.lr = 0.01
+    coord = torch.from_numpy(case["coord"]).to(DEV); label = torch.from_numpy(case["label"]).to(DEV)
+    tr = SdfTrainer(cfg, octree, dec)
+    tr.zero_grad()
+    first = float(tr.train_step(coord, label))
+    for _ in range(60):
+        last = float(tr.train_step(coord, label))
+    assert last < 0.9 * first, (first, last)
+
+
+def test_cpu_tensor_is_rejected_loudly():
+    from shine_mapping_b200 import _abi
+    case = make_case(n_points=1500, n_batch=10, feat_levels=2, seed=5)
+    cfg, octree, dec = build_cuda_models(case, DEV)
+    with pytest.raises(_abi.ShineB200Error):
+        octree.query_feature(torch.zeros(4, 3))
+
+
+def test_abi_rejects_bad_arguments():
+    from shine_mapping_b200 import _abi
+    lib = _abi.lib()
+    d = _abi.ShineOctree()
+    d.num_levels = 0
+    assert lib.shine_query_fwd(C.byref(d), None, 4, None, None) == -1
+    assert b"invalid" in lib.shine_error_string(-1)
