@@ -1,0 +1,111 @@
+"""Batch-mode mapping loop — the caller side of the hot path, after reference shine_batch.py:23-233.
+
+    python -m shine_mapping_b200.batch_loop config.yaml [--synthetic-azimuth 2048 --frames 10]
+
+Same sequence as the reference loop (T-points of shine_batch.py:107-212 kept as timing keys): build the octree
+from all frames, set up the optimiser, then `iters` x { lr decay -> get_batch -> fwd+loss+bwd -> optimiser },
+checkpoint in the reference's format.  What differs: the body of an iteration is TWO launches (the fused
+`shine_sdf_bce_step` kernel and the multi-tensor Adam kernel, which also re-zeroes the gradients) instead of
+~300, and there is no host round trip inside the loop (loss is read back only when logging).
+
+Out of scope here: dataset I/O (open3d), meshing, visualiser, wandb.  `pool` is anything with the
+`get_batch(bs)` contract of LiDARDataset (dataset/lidar_dataset.py:431-448); `synth.build_scene_map` provides one.
+Configs that need d(pred)/d(coord) (ekional_loss_on etc.) or another loss are rejected explicitly.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import time
+
+import torch
+
+from .config import SHINEConfig
+from .decoder import Decoder
+from .feature_octree import FeatureOctree
+from .trainer import SdfTrainer
+
+
+def check_supported(config: SHINEConfig) -> None:
+    unsupported = [k for k in ("ekional_loss_on", "normal_loss_on", "consistency_loss_on", "proj_correction_on",
+                               "semantic_on", "time_conditioned", "ray_loss") if getattr(config, k)]
+    if unsupported or config.main_loss_type != "sdf_bce":
+        raise NotImplementedError(
+            f"the fused sm_100a step implements main_loss_type=sdf_bce without {unsupported or 'extras'}; "
+            "reference configs that switch these on (e.g. kitti_batch.yaml ekional_loss_on) must turn them off")
+    if not config.opt_adam:
+        raise NotImplementedError("only Adam (reference utils/tools.py:78-79) is implemented")
+
+
+def step_lr_decay(trainer: SdfTrainer, base_lr: float, iteration: int, steps, ratio: float) -> None:
+    """Step decay of reference utils/tools.py:135-155: lr = base * ratio^(number of milestones passed)."""
+    passed = sum(1 for s in steps if iteration >= s)
+    trainer.lr = base_lr * (ratio ** passed)
+
+
+def save_checkpoint(octree, decoder, trainer, run_path, name, iters):
+    """Same dict layout as reference utils/tools.py:200-213 (whole octree module pickled, decoder state_dict)."""
+    os.makedirs(os.path.join(run_path, "model"), exist_ok=True)
+    torch.save({"iters": iters, "feature_octree": octree, "geo_decoder": decoder.state_dict(),
+                "optimizer": {"exp_avg": trainer.exp_avg, "exp_avg_sq": trainer.exp_avg_sq,
+                              "step": trainer.step_count}},
+               os.path.join(run_path, f"{name}.pth"))
+
+
+def run_shine_mapping_batch(config: SHINEConfig, octree: FeatureOctree, decoder: Decoder, pool, iters=None,
+                            log_every: int = 0, run_path: str | None = None, process_group=None,
+                            shard_mode: str = "replicated"):
+    """-> dict(loss_first, loss_last, points_per_s, timing).  `octree` must already hold the map of `pool`."""
+    check_supported(config)
+    dev = octree.hier_features[0].device
+    trainer = SdfTrainer(config, octree, decoder, process_group=process_group, shard_mode=shard_mode)
+    world = torch.distributed.get_world_size(process_group) if torch.distributed.is_initialized() else 1
+    iters = config.iters if iters is None else iters
+    trainer.zero_grad()
+    losses = {}
+    timing = {"load": 0.0, "step": 0.0}
+    t_begin = None
+    for it in range(iters):
+        if it == min(3, iters - 1):       # skip warm-up iterations in the throughput figure
+            torch.cuda.synchronize(dev); t_begin = time.perf_counter(); it_begin = it
+        step_lr_decay(trainer, config.lr, it, config.lr_decay_step, config.lr_iters_reduce_ratio)
+        coord, sdf_label, weight = pool.get_batch(config.bs)                       # shine_batch.py:115
+        trainer.forward_backward(coord, sdf_label, weight, n_norm=config.bs * world)   # :123-209
+        trainer.all_reduce_grads()
+        trainer.optimizer_step(zero_grad=True)                                      # :208-210
+        if it == 0 or it == iters - 1 or (log_every and it % log_every == 0):
+            losses[it] = float(trainer.loss)          # the only host read-back
+        if run_path and ((it + 1) % config.save_freq_iters == 0) and it > 0:
+            save_checkpoint(octree, decoder, trainer, run_path, f"model/model_iter_{it + 1}", it)
+    torch.cuda.synchronize(dev)
+    elapsed = time.perf_counter() - t_begin if t_begin is not None else float("nan")
+    done = iters - it_begin if t_begin is not None else 0
+    return {"loss_first": losses.get(0), "loss_last": losses.get(iters - 1), "losses": losses,
+            "iters_per_s": done / elapsed if done else None,
+            "points_per_s": done * config.bs * world / elapsed if done else None, "timing": timing}
+
+
+def main(argv=None):
+    import argparse
+    from . import synth
+    ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
+    ap.add_argument("config")
+    ap.add_argument("--synthetic-azimuth", type=int, default=2048)
+    ap.add_argument("--frames", type=int, default=10)
+    ap.add_argument("--iters", type=int, default=None)
+    args = ap.parse_args(argv)
+    config = SHINEConfig()
+    config.load(args.config)
+    config.ekional_loss_on = False      # see check_supported()
+    torch.manual_seed(config.seed)
+    octree, decoder = FeatureOctree(config), Decoder(config)
+    print("Load, preprocess and sample data (synthetic scans)")
+    pool = synth.build_scene_map(config, octree, args.synthetic_azimuth, args.frames, seed=config.seed)
+    octree.print_detail()
+    print("Begin mapping")
+    out = run_shine_mapping_batch(config, octree, decoder, pool, iters=args.iters, log_every=1000)
+    print({k: v for k, v in out.items() if k != "losses"})
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,82 @@
+"""The shine_batch.py-equivalent loop and the multi-GPU step on real devices."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from tests.parity_utils import build_cuda_models, make_case, make_config, run_oracle_step
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_batch_loop_trains_and_checkpoints(tmp_path, built_lib):
+    from shine_mapping_b200 import Decoder, FeatureOctree, synth
+    from shine_mapping_b200.batch_loop import check_supported, run_shine_mapping_batch
+    cfg = make_config(4, device=DEV, bs=4096, lr=0.01, iters=300, weight_decay=1e-7, save_freq_iters=300)
+    torch.manual_seed(42)
+    octree, decoder = FeatureOctree(cfg), Decoder(cfg)
+    pool = synth.build_scene_map(cfg, octree, n_azimuth=256, n_frames=2, seed=42, device=DEV)
+    out = run_shine_mapping_batch(cfg, octree, decoder, pool, run_path=str(tmp_path))
+    assert out["loss_last"] < 0.8 * out["loss_first"], out
+    assert out["points_per_s"] > 1e6
+    ck = torch.load(tmp_path / "model" / "model_iter_300.pth", weights_only=False)   # reference checkpoint layout
+    assert set(ck) >= {"iters", "feature_octree", "geo_decoder", "optimizer"}
+    restored = ck["feature_octree"]
+    coord, _, _ = pool.get_batch(1000)
+    assert torch.equal(restored.query_feature(coord), octree.query_feature(coord))    # hash rebuilt after unpickle
+    cfg.ekional_loss_on = True
+    with pytest.raises(NotImplementedError):
+        check_supported(cfg)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _dp_worker(rank, world, port, out_dir):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    from shine_mapping_b200 import SdfTrainer, dist as sdist
+    sdist.init_from_env("nccl")
+    dev = f"cuda:{rank}"
+    case = make_case(n_points=2500, n_batch=6000, feat_levels=4, seed=51)
+    cfg, octree, dec = build_cuda_models(case, dev)
+    n = case["coord"].shape[0]
+    b, e = sdist.shard_range(n, rank, world)
+    coord = torch.from_numpy(case["coord"][b:e]).to(dev); label = torch.from_numpy(case["label"][b:e]).to(dev)
+    tr = SdfTrainer(cfg, octree, dec, shard_mode="replicated")
+    tr.zero_grad()
+    loss = tr.forward_backward(coord, label, n_norm=n).clone()
+    tr.all_reduce_grads()
+    sdist.all_reduce_sum(loss)
+    torch.cuda.synchronize()
+    if rank == 0:
+        np.save(os.path.join(out_dir, "flat.npy"), tr.flat_grad.cpu().numpy())
+        np.save(os.path.join(out_dir, "loss.npy"), loss.cpu().numpy())
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_gpu_data_parallel_matches_oracle(tmp_path, built_lib):
+    """Point batch sharded over 2 GPUs + ONE NCCL all-reduce of the flat gradient == oracle gradient of the batch."""
+    import torch.multiprocessing as mp
+    mp.spawn(_dp_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / "flat.npy")
+    case = make_case(n_points=2500, n_batch=6000, feat_levels=4, seed=51)
+    want = run_oracle_step(case)
+    off = 0
+    for g in want["table_grads"]:
+        seg = got[off:off + g.size].reshape(g.shape)
+        assert np.abs(seg[:-1] - g[:-1]).max() <= 2e-4 * np.abs(g).max() + 1e-10
+        off += (g.size + 3) & ~3
+    for k in ["layers.0.weight", "layers.0.bias", "layers.1.weight", "layers.1.bias", "lout.weight", "lout.bias"]:
+        g = want["dec_grads"][k]
+        seg = got[off:off + g.size].reshape(g.shape)
+        assert np.abs(seg - g).max() <= 2e-4 * np.abs(g).max() + 1e-10, k
+        off += (g.size + 3) & ~3
+    assert abs(float(np.load(tmp_path / "loss.npy")) - want["loss"]) <= 2e-5 * abs(want["loss"])
