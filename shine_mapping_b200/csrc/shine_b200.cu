@@ -28,6 +28,9 @@
 #ifndef SHINE_PARALLEL_PROBE
 #define SHINE_PARALLEL_PROBE 0 // issue every level's first-probe key load before resolving any (costs registers)
 #endif
+#ifndef SHINE_HASH32
+#define SHINE_HASH32 0        // 32-bit fmix32 hash of the folded key (else the 64-bit two-multiply mix)
+#endif
 #ifndef SHINE_PREFETCH
 #define SHINE_PREFETCH 1      // software-pipeline the next tile's coord/label loads
 #endif
@@ -35,7 +38,7 @@
 #define SHINE_TRAIN_MINB 2    // min resident blocks/SM of the training kernel (register cap 65536/(256*MINB))
 #endif
 #ifndef SHINE_INFER_MINB
-#define SHINE_INFER_MINB 4
+#define SHINE_INFER_MINB 3
 #endif
 
 namespace {
@@ -60,12 +63,19 @@ struct __align__(64) HashSlot {
 static_assert(sizeof(HashSlot) == SHINE_HASH_SLOT_BYTES, "slot must be 64 bytes");
 
 __host__ __device__ __forceinline__ uint32_t hash_key(unsigned long long k) {
-    k ^= k >> 31;
-    k *= 0x9E3779B97F4A7C15ull;
-    k ^= k >> 29;
-    k *= 0xBF58476D1CE4E5B9ull;
+#if SHINE_HASH32
+    // 32-bit finaliser (murmur3 fmix32) over the folded key: ~9 integer ops instead of two 64-bit multiplies
+    uint32_t x = (uint32_t)k ^ ((uint32_t)(k >> 32) * 0x9E3779B1u);
+    x ^= x >> 16; x *= 0x85EBCA6Bu;
+    x ^= x >> 13; x *= 0xC2B2AE35u;
+    x ^= x >> 16;
+    return x;
+#else
+    k ^= k >> 31; k *= 0x9E3779B97F4A7C15ull;
+    k ^= k >> 29; k *= 0xBF58476D1CE4E5B9ull;
     k ^= k >> 32;
     return (uint32_t)k;
+#endif
 }
 
 // bit i of v -> bit 3i (16 significant bits, as kaolin's int16 coordinates)
@@ -116,6 +126,12 @@ struct Blend {   // the 8 weights of model/feature_octree.py:186-193, corner c =
 
 __device__ __forceinline__ float4 ldg_f4(const float* p) {
     return __ldg(reinterpret_cast<const float4*>(p));
+}
+// one instruction per full 32-byte feature row (sm_100a LDG.E.ENL2.256)
+__device__ __forceinline__ void ldg_row8(const float* p, float (&v)[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
 }
 __device__ __forceinline__ int4 ldg_i4(const int32_t* p) {
     return __ldg(reinterpret_cast<const int4*>(p));
@@ -342,6 +358,51 @@ __device__ __forceinline__ void from_cfrag(const float (&c)[4], int odd, float (
 }
 
 // ------------------------------------------------------------------------------------------------------
+// Tensor Memory as accumulator parking space.  The decoder-gradient accumulators (56 fp32 per lane: dW2 32,
+// dW1 8, db2 8, db1 8) are only touched in the wgrad section of a tile; between tiles they live in TMEM
+// (tcgen05.st / tcgen05.ld -> SASS STTM / LDTM) instead of pinning registers through the gather and MLP phases.
+// Warp w of the block owns TMEM lanes 32*(w&3).. and columns 64*(w>>2)..+55 of the block's 128-column allocation.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=f"(v[0]),"=f"(v[1]),"=f"(v[2]),"=f"(v[3]),"=f"(v[4]),"=f"(v[5]),"=f"(v[6]),"=f"(v[7]),"=f"(v[8]),"=f"(v[9]),"=f"(v[10]),"=f"(v[11]),"=f"(v[12]),"=f"(v[13]),"=f"(v[14]),"=f"(v[15]),"=f"(v[16]),"=f"(v[17]),"=f"(v[18]),"=f"(v[19]),"=f"(v[20]),"=f"(v[21]),"=f"(v[22]),"=f"(v[23]),"=f"(v[24]),"=f"(v[25]),"=f"(v[26]),"=f"(v[27]),"=f"(v[28]),"=f"(v[29]),"=f"(v[30]),"=f"(v[31]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=f"(v[0]),"=f"(v[1]),"=f"(v[2]),"=f"(v[3]),"=f"(v[4]),"=f"(v[5]),"=f"(v[6]),"=f"(v[7]),"=f"(v[8]),"=f"(v[9]),"=f"(v[10]),"=f"(v[11]),"=f"(v[12]),"=f"(v[13]),"=f"(v[14]),"=f"(v[15]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]),"=f"(v[1]),"=f"(v[2]),"=f"(v[3]),"=f"(v[4]),"=f"(v[5]),"=f"(v[6]),"=f"(v[7]) : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                 :: "r"(taddr), "f"(v[0]),"f"(v[1]),"f"(v[2]),"f"(v[3]),"f"(v[4]),"f"(v[5]),"f"(v[6]),"f"(v[7]),"f"(v[8]),"f"(v[9]),"f"(v[10]),"f"(v[11]),"f"(v[12]),"f"(v[13]),"f"(v[14]),"f"(v[15]),"f"(v[16]),"f"(v[17]),"f"(v[18]),"f"(v[19]),"f"(v[20]),"f"(v[21]),"f"(v[22]),"f"(v[23]),"f"(v[24]),"f"(v[25]),"f"(v[26]),"f"(v[27]),"f"(v[28]),"f"(v[29]),"f"(v[30]),"f"(v[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 :: "r"(taddr), "f"(v[0]),"f"(v[1]),"f"(v[2]),"f"(v[3]),"f"(v[4]),"f"(v[5]),"f"(v[6]),"f"(v[7]),"f"(v[8]),"f"(v[9]),"f"(v[10]),"f"(v[11]),"f"(v[12]),"f"(v[13]),"f"(v[14]),"f"(v[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(taddr), "f"(v[0]),"f"(v[1]),"f"(v[2]),"f"(v[3]),"f"(v[4]),"f"(v[5]),"f"(v[6]),"f"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// register view: dW2[2][4][4] (cols 0..31), dW1[2][4] (32..39), db2[4][2] (40..47), db1[4][2] (48..55)
+#define SHINE_ACC_DECL float dW2[2][4][4], dW1[2][4], db2p[4][2], db1p[4][2]
+#define SHINE_ACC_LOAD(ta)                                                                             \
+    do {                                                                                               \
+        tmem_ld32((ta), &dW2[0][0][0]); tmem_ld8((ta) + 32, &dW1[0][0]); tmem_ld8((ta) + 40, &db2p[0][0]); \
+        tmem_ld8((ta) + 48, &db1p[0][0]); tmem_wait_ld();                                                \
+    } while (0)
+#define SHINE_ACC_STORE(ta)                                                                            \
+    do {                                                                                               \
+        tmem_st32((ta), &dW2[0][0][0]); tmem_st8((ta) + 32, &dW1[0][0]); tmem_st8((ta) + 40, &db2p[0][0]); \
+        tmem_st8((ta) + 48, &db1p[0][0]); tmem_wait_st();                                                \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------
 // the fused kernel: hash walk + gather + blend + MLP (+ BCE loss) (+ full backward with scatter-add)
 // ------------------------------------------------------------------------------------------------------
 
@@ -376,7 +437,7 @@ struct SmemPlan {
     static constexpr int RED = B3 + 4;                 // block accumulator for decoder grads [1377 -> 1380]
     static constexpr int kDecGradFloats = kH * kF + kH + kH * kH + kH + kH + 1;   // 1377
     static constexpr int STAGE = RED + 1380;           // per-warp staging: 2 x [16][kWS] + [16][8]
-    static constexpr int kStagePerWarp = 2 * kTile * kWS + kTile * kF;
+    static constexpr int kStagePerWarp = 3 * kTile * kWS + kTile * kF;   // dh2 | h1 | dh1 | feat tiles
 };
 
 template <int NTF, bool TRAIN, bool DEC_GRAD, int LMAX>
@@ -407,16 +468,20 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
     }
     if (tid == 0) smem[SmemPlan::B3] = P.dec.b3 ? P.dec.b3[0] : 0.f;
     if (DEC_GRAD) for (int i = tid; i < 1380; i += blockDim.x) smem[SmemPlan::RED + i] = 0.f;
-    __syncthreads();
-
-    const bool poly = P.oct.poly_interp != 0;
-    const int L = P.oct.num_levels;
-    const float up = (TRAIN && P.d_loss) ? __ldg(P.d_loss) : 1.0f;
-    const float gscale = P.loss_scale * up;
-
-    // persistent decoder-gradient accumulators (C-fragment layout), reduced once at the end
-    float dW2[2][4][4], dW1[2][4], db2p[4][2], db1p[4][2], dw3p[4][2], db3p = 0.f;
+    uint32_t tacc = 0;   // this warp's TMEM parking area
     if (DEC_GRAD) {
+        if (warp == 0) {   // one warp allocates 128 columns for the block (2 blocks/SM -> 256 of 512)
+            const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smu + SmemPlan::B3 + 1);
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(sa) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (DEC_GRAD) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tacc = smu[SmemPlan::B3 + 1] + ((uint32_t)(32 * (warp & 3)) << 16) + 64u * (uint32_t)(warp >> 2);
+        SHINE_ACC_DECL;
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
 #pragma unroll
@@ -424,14 +489,27 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
             dW1[a][0] = dW1[a][1] = dW1[a][2] = dW1[a][3] = 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { db2p[j][0] = db2p[j][1] = db1p[j][0] = db1p[j][1] = dw3p[j][0] = dw3p[j][1] = 0.f; }
+        for (int j = 0; j < 4; ++j) { db2p[j][0] = db2p[j][1] = db1p[j][0] = db1p[j][1] = 0.f; }
+        SHINE_ACC_STORE(tacc);
     }
+
+    const bool poly = P.oct.poly_interp != 0;
+    const int L = P.oct.num_levels;
+    const float up = (TRAIN && P.d_loss) ? __ldg(P.d_loss) : 1.0f;
+    const float gscale = P.loss_scale * up;
+
+    // decoder-gradient accumulators: dW2/dW1/db2/db1 are parked in TMEM (see DecGradAcc); only the 9 values of the
+    // output layer stay in registers
+    float dw3p[4][2], db3p = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { dw3p[j][0] = dw3p[j][1] = 0.f; }
     float loss_acc = 0.f;
 
     float* stage = smem + SmemPlan::STAGE + warp * SmemPlan::kStagePerWarp;   // only touched when DEC_GRAD
     float* stA = stage;                       // [16][kWS]
     float* stB = stage + kTile * kWS;         // [16][kWS]
-    float* stX = stage + 2 * kTile * kWS;     // [16][8]
+    float* stC = stage + 2 * kTile * kWS;     // [16][kWS]
+    float* stX = stage + 3 * kTile * kWS;     // [16][8]
 
     const int warp_global = blockIdx.x * kWarps + warp;
     const int warp_stride = gridDim.x * kWarps;
@@ -471,88 +549,85 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
 
         // ---- hash walk (model/feature_octree.py:199-218): all levels probed in parallel, the 8 corner ids are
         //      fetched speculatively with the key (same 64-byte slot) so a first-probe hit costs ONE latency ----
+        // ---- hash walk (model/feature_octree.py:199-218).  The two lanes of a point split the LEVELS: lane `half`
+        //      probes levels half, half+2, ... (first-probe keys of all its levels in flight together), then the
+        //      pair exchanges slot indices.  Serial dependent probes per lane: 1 instead of L. ----
         int slot[LMAX];
-#if SHINE_PARALLEL_PROBE
-        int4 ia[LMAX], ib[LMAX];
         {
-            unsigned long long kq[LMAX], kf[LMAX];
+            constexpr int LH = LMAX / 2;
             const unsigned long long key0 = valid ? morton_of(x, y, z, P.oct.lv[0].level) : 0ull;
+            unsigned long long kq[LH], kf[LH];
+            int mine[LH];
 #pragma unroll
-            for (int i = 0; i < LMAX; ++i) {
-                slot[i] = -1;
+            for (int j = 0; j < LH; ++j) {
+                const int i = 2 * j + half;
+                mine[j] = -1;
                 if (i < L && valid) {
                     const shine_level& lv = P.oct.lv[i];
                     const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
-                    kq[i] = consecutive ? (key0 >> (3 * i)) : morton_of(x, y, z, lv.level);
-                    const uint32_t h = hash_key(kq[i]) & (lv.hash_capacity - 1);
-                    slot[i] = (int)h;
-                    kf[i] = __ldg(&slots[h].key);
-#if SHINE_SPEC_IDS
-                    ia[i] = ldg_i4(slots[h].ids); ib[i] = ldg_i4(slots[h].ids + 4);
-#endif
+                    kq[j] = consecutive ? (key0 >> (3 * i)) : morton_of(x, y, z, lv.level);
+                    mine[j] = (int)(hash_key(kq[j]) & (lv.hash_capacity - 1));
+                    kf[j] = __ldg(&slots[mine[j]].key);
                 }
             }
 #pragma unroll
-            for (int i = 0; i < LMAX; ++i) {
-                if (i < L && valid) {
-                    if (kf[i] != kq[i]) {
-                        if (kf[i] == kEmptyKey) {
-                            slot[i] = -1;
-                        } else {   // collision on the first probe (rare at load factor <= 0.5): walk on
-                            const shine_level& lv = P.oct.lv[i];
-                            const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
-                            slot[i] = probe_slot_from(slots, lv.hash_capacity - 1, kq[i], (uint32_t)slot[i] + 1);
-#if SHINE_SPEC_IDS
-                            if (slot[i] >= 0) { ia[i] = ldg_i4(slots[slot[i]].ids); ib[i] = ldg_i4(slots[slot[i]].ids + 4); }
-#endif
-                        }
+            for (int j = 0; j < LH; ++j) {
+                const int i = 2 * j + half;
+                if (i < L && valid && kf[j] != kq[j]) {
+                    if (kf[j] == kEmptyKey) {
+                        mine[j] = -1;
+                    } else {   // first-probe collision (rare at load factor <= 0.5): walk on
+                        const shine_level& lv = P.oct.lv[i];
+                        mine[j] = probe_slot_from(reinterpret_cast<const HashSlot*>(lv.hash_slots),
+                                                  lv.hash_capacity - 1, kq[j], (uint32_t)mine[j] + 1);
                     }
                 }
             }
-        }
-#else
-        {
-            const unsigned long long key0 = valid ? morton_of(x, y, z, P.oct.lv[0].level) : 0ull;
+            __syncwarp();
 #pragma unroll
-            for (int i = 0; i < LMAX; ++i) {
-                slot[i] = -1;
-                if (i < L && valid) {
-                    const shine_level& lv = P.oct.lv[i];
-                    const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
-                    const unsigned long long kq = consecutive ? (key0 >> (3 * i)) : morton_of(x, y, z, lv.level);
-                    slot[i] = probe_slot(slots, lv.hash_capacity - 1, kq);
-                }
+            for (int j = 0; j < LH; ++j) {
+                const int other = __shfl_xor_sync(kFull, mine[j], 2);
+                slot[2 * j] = half ? other : mine[j];
+                slot[2 * j + 1] = half ? mine[j] : other;
             }
         }
-#endif
 
-        // ---- 8-corner gather + blend, summed over levels (model/feature_octree.py:222-234) --------------------
-        float feat[4] = {0.f, 0.f, 0.f, 0.f};
+        // ---- 8-corner gather + blend, summed over levels (model/feature_octree.py:222-234).  The pair splits the
+        //      CORNERS: lane `half` fetches corners 4*half..4*half+3 as whole 32-byte rows (one LDG.256 each) and
+        //      blends all 8 channels; the two partial sums are then exchanged so that each lane ends with the 4
+        //      channels of its row-half. ----
+        float feat[4];
+        {
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < LMAX; ++i) {
-            if (i < L && slot[i] >= 0) {
-                const shine_level& lv = P.oct.lv[i];
-                const float* fb = lv.features + 4 * half;
-#if SHINE_PARALLEL_PROBE && SHINE_SPEC_IDS
-                const int4 ja = ia[i], jb = ib[i];
-#else
-                const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
-                const int4 ja = ldg_i4(slots[slot[i]].ids), jb = ldg_i4(slots[slot[i]].ids + 4);
-#endif
-                float4 v[8];
-                v[0] = ldg_f4(fb + (int64_t)ja.x * kF); v[1] = ldg_f4(fb + (int64_t)ja.y * kF);
-                v[2] = ldg_f4(fb + (int64_t)ja.z * kF); v[3] = ldg_f4(fb + (int64_t)ja.w * kF);
-                v[4] = ldg_f4(fb + (int64_t)jb.x * kF); v[5] = ldg_f4(fb + (int64_t)jb.y * kF);
-                v[6] = ldg_f4(fb + (int64_t)jb.z * kF); v[7] = ldg_f4(fb + (int64_t)jb.w * kF);
-                Blend b; b.init(x, y, z, lv.level, poly);
-                float4 ls = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < LMAX; ++i) {
+                if (i < L && slot[i] >= 0) {
+                    const shine_level& lv = P.oct.lv[i];
+                    const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
+                    const int4 id4 = ldg_i4(slots[slot[i]].ids + 4 * half);
+                    float r0[8], r1[8], r2[8], r3[8];
+                    ldg_row8(lv.features + (int64_t)id4.x * kF, r0);
+                    ldg_row8(lv.features + (int64_t)id4.y * kF, r1);
+                    ldg_row8(lv.features + (int64_t)id4.z * kF, r2);
+                    ldg_row8(lv.features + (int64_t)id4.w * kF, r3);
+                    Blend b; b.init(x, y, z, lv.level, poly);
+                    const float wx = half ? b.tx : b.ux;            // corner bit 2 (x) is this lane's `half`
+                    const float wxy0 = __fmul_rn(wx, b.uy), wxy1 = __fmul_rn(wx, b.ty);
+                    const float w0 = __fmul_rn(wxy0, b.uz), w1 = __fmul_rn(wxy0, b.tz);
+                    const float w2 = __fmul_rn(wxy1, b.uz), w3 = __fmul_rn(wxy1, b.tz);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float w = b.w(c);
-                    ls.x = fmaf(w, v[c].x, ls.x); ls.y = fmaf(w, v[c].y, ls.y);
-                    ls.z = fmaf(w, v[c].z, ls.z); ls.w = fmaf(w, v[c].w, ls.w);
+                    for (int q = 0; q < 8; ++q) {
+                        float a = acc[q];
+                        a = fmaf(w0, r0[q], a); a = fmaf(w1, r1[q], a); a = fmaf(w2, r2[q], a); a = fmaf(w3, r3[q], a);
+                        acc[q] = a;
+                    }
                 }
-                feat[0] += ls.x; feat[1] += ls.y; feat[2] += ls.z; feat[3] += ls.w;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float send = half ? acc[q] : acc[4 + q];
+                const float recv = __shfl_xor_sync(kFull, send, 2);
+                feat[q] = (half ? acc[4 + q] : acc[q]) + recv;
             }
         }
         if (!TRAIN && P.mask) {
@@ -568,7 +643,12 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
             float a[4]; to_afrag(feat, odd, a);
             ax.set(a[0], a[1], a[2], a[3]);
         }
+        // operands of the weight-gradient contraction go to this warp's shared-memory staging the moment they are
+        // produced (feat -> stX, h1 -> stB, dh2 -> stA, dh1 -> stC) so that they do not pin registers
+        if (DEC_GRAD)
+            *reinterpret_cast<float4*>(stX + (g + 8 * odd) * kF + 4 * half) = make_float4(feat[0], feat[1], feat[2], feat[3]);
         float h1[4][4];
+        uint32_t m1 = 0;   // ReLU mask of h1: bit 4j+r
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const float bA = smem[SmemPlan::B1 + 8 * j + 2 * t], bB = smem[SmemPlan::B1 + 8 * j + 2 * t + 1];
@@ -578,7 +658,14 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
             const uint2 bl = *reinterpret_cast<const uint2*>(smu + SmemPlan::W1 + kH * kF + off);
             mma3<NTF>(c, ax, bh, bl);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) h1[j][r] = fmaxf(c[r], 0.f);
+            for (int r = 0; r < 4; ++r) {
+                h1[j][r] = fmaxf(c[r], 0.f);
+                if (TRAIN && c[r] > 0.f) m1 |= 1u << (4 * j + r);
+            }
+            if (DEC_GRAD) {
+                *reinterpret_cast<float2*>(stB + g * kWS + 8 * j + 2 * t) = make_float2(h1[j][0], h1[j][1]);
+                *reinterpret_cast<float2*>(stB + (g + 8) * kWS + 8 * j + 2 * t) = make_float2(h1[j][2], h1[j][3]);
+            }
         }
         float h2[4][4];
         {
@@ -636,13 +723,16 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         const float dpx = __shfl_xor_sync(kFull, dpo, 1);
         const float dp0 = odd ? dpx : dpo, dp8 = odd ? dpo : dpx;
         float dh2[4][4];
+        float db2t[4][2], db1t[4][2];   // this tile's bias-gradient partials, folded into TMEM in the wgrad section
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             dh2[j][0] = h2[j][0] > 0.f ? dp0 * w3a[j] : 0.f; dh2[j][1] = h2[j][1] > 0.f ? dp0 * w3b[j] : 0.f;
             dh2[j][2] = h2[j][2] > 0.f ? dp8 * w3a[j] : 0.f; dh2[j][3] = h2[j][3] > 0.f ? dp8 * w3b[j] : 0.f;
             if (DEC_GRAD) {
                 dw3p[j][0] += dp0 * h2[j][0] + dp8 * h2[j][2]; dw3p[j][1] += dp0 * h2[j][1] + dp8 * h2[j][3];
-                db2p[j][0] += dh2[j][0] + dh2[j][2];           db2p[j][1] += dh2[j][1] + dh2[j][3];
+                db2t[j][0] = dh2[j][0] + dh2[j][2];            db2t[j][1] = dh2[j][1] + dh2[j][3];
+                *reinterpret_cast<float2*>(stA + g * kWS + 8 * j + 2 * t) = make_float2(dh2[j][0], dh2[j][1]);
+                *reinterpret_cast<float2*>(stA + (g + 8) * kWS + 8 * j + 2 * t) = make_float2(dh2[j][2], dh2[j][3]);
             }
         }
         if (DEC_GRAD && t == 0) db3p += dp0 + dp8;
@@ -663,8 +753,12 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                     mma3<NTF>(c, ad[kk], bh, bl);
                 }
 #pragma unroll
-                for (int r = 0; r < 4; ++r) dh1[j][r] = h1[j][r] > 0.f ? c[r] : 0.f;
-                if (DEC_GRAD) { db1p[j][0] += dh1[j][0] + dh1[j][2]; db1p[j][1] += dh1[j][1] + dh1[j][3]; }
+                for (int r = 0; r < 4; ++r) dh1[j][r] = ((m1 >> (4 * j + r)) & 1u) ? c[r] : 0.f;
+                if (DEC_GRAD) {
+                    db1t[j][0] = dh1[j][0] + dh1[j][2]; db1t[j][1] = dh1[j][1] + dh1[j][3];
+                    *reinterpret_cast<float2*>(stC + g * kWS + 8 * j + 2 * t) = make_float2(dh1[j][0], dh1[j][1]);
+                    *reinterpret_cast<float2*>(stC + (g + 8) * kWS + 8 * j + 2 * t) = make_float2(dh1[j][2], dh1[j][3]);
+                }
             }
         }
         float dxc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -681,14 +775,13 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
 
         // ---- backward: decoder weight grads (contraction over the tile's 16 points) -------------------
         if (DEC_GRAD) {
+            SHINE_ACC_DECL;
+            SHINE_ACC_LOAD(tacc);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                *reinterpret_cast<float2*>(stA + g * kWS + 8 * j + 2 * t) = make_float2(dh2[j][0], dh2[j][1]);
-                *reinterpret_cast<float2*>(stA + (g + 8) * kWS + 8 * j + 2 * t) = make_float2(dh2[j][2], dh2[j][3]);
-                *reinterpret_cast<float2*>(stB + g * kWS + 8 * j + 2 * t) = make_float2(h1[j][0], h1[j][1]);
-                *reinterpret_cast<float2*>(stB + (g + 8) * kWS + 8 * j + 2 * t) = make_float2(h1[j][2], h1[j][3]);
+                db2p[j][0] += db2t[j][0]; db2p[j][1] += db2t[j][1];
+                db1p[j][0] += db1t[j][0]; db1p[j][1] += db1t[j][1];
             }
-            *reinterpret_cast<float4*>(stX + (g + 8 * odd) * kF + 4 * half) = make_float4(feat[0], feat[1], feat[2], feat[3]);
             __syncwarp();
             // dW2[n2][k1] += sum_rows dh2[row][n2] * h1[row][k1]
 #pragma unroll
@@ -708,14 +801,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                     for (int nt = 0; nt < 4; ++nt) mma3<NTF>(dW2[mt][nt], a, bh[nt], bl[nt]);
                 }
             }
-            __syncwarp();
             // dW1[n1][ch] += sum_rows dh1[row][n1] * feat[row][ch]
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                *reinterpret_cast<float2*>(stA + g * kWS + 8 * j + 2 * t) = make_float2(dh1[j][0], dh1[j][1]);
-                *reinterpret_cast<float2*>(stA + (g + 8) * kWS + 8 * j + 2 * t) = make_float2(dh1[j][2], dh1[j][3]);
-            }
-            __syncwarp();
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
                 uint2 bh, bl;
@@ -724,12 +810,13 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
                     AFrag<NTF> a;
-                    a.set(stA[(8 * ks + t) * kWS + 16 * mt + g], stA[(8 * ks + t) * kWS + 16 * mt + g + 8],
-                          stA[(8 * ks + t + 4) * kWS + 16 * mt + g], stA[(8 * ks + t + 4) * kWS + 16 * mt + g + 8]);
+                    a.set(stC[(8 * ks + t) * kWS + 16 * mt + g], stC[(8 * ks + t) * kWS + 16 * mt + g + 8],
+                          stC[(8 * ks + t + 4) * kWS + 16 * mt + g], stC[(8 * ks + t + 4) * kWS + 16 * mt + g + 8]);
                     mma3<NTF>(dW1[mt], a, bh, bl);
                 }
             }
             __syncwarp();
+            SHINE_ACC_STORE(tacc);
         }
 
         // ---- backward: scatter-add into the corner-feature tables (index_put_ accumulate) -------------
@@ -760,6 +847,8 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         if (lane == 0 && loss_acc != 0.f) atomicAdd(P.loss, loss_acc * P.loss_scale);
     }
     if (DEC_GRAD) {
+        SHINE_ACC_DECL;
+        SHINE_ACC_LOAD(tacc);
         float* red = smem + SmemPlan::RED;   // [gw1 256 | gb1 32 | gw2 1024 | gb2 32 | gw3 32 | gb3 1]
         constexpr int oW1 = 0, oB1 = 256, oW2 = 288, oB2 = 1312, oW3 = 1344, oB3 = 1376;
 #pragma unroll
@@ -807,6 +896,12 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
             else if (i < oB3) dst = P.dec.gw3 + (i - oW3);
             else dst = P.dec.gb3;
             if (dst) atomicAdd(dst, v);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (warp == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(smu[SmemPlan::B3 + 1]) : "memory");
         }
     }
 }
@@ -937,6 +1032,16 @@ int launch_fused_t(const StepParams& P, cudaStream_t st) {
         int q = 1;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, 256, smem_bytes);
         if (e != cudaSuccess) return (int)e;
+        // the API is conservative about the shared-memory carve-out; the tile loop is grid-size agnostic, so size the
+        // grid from the hardware limits directly (64K registers, 227 KB usable shared memory + 1 KB/block reserved)
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, kern);
+        if (e != cudaSuccess) return (int)e;
+        const int by_regs = fa.numRegs > 0 ? 65536 / (fa.numRegs * 256) : 1;
+        const int by_smem = (int)((227 * 1024) / (smem_bytes + 1024));
+        int own = by_regs < by_smem ? by_regs : by_smem;
+        if (own > 8) own = 8;
+        if (own > q) q = own;
         per_sm_cached = q < 1 ? 1 : q;
     }
     const int per_sm = per_sm_cached;

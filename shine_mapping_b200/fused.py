@@ -66,12 +66,11 @@ class _SdfBce(torch.autograd.Function):
         if want_grad and single_pass:
             tgrads = [torch.zeros_like(p) for p in tables]
             dgrads = [torch.zeros_like(p) if (p is not None and any(need_d)) else None for p in dparams]
-            od = octree._descriptor(tables, tgrads, n_points=n)
+            od = octree._descriptor(tables, tgrads)
             dd = decoder.c_descriptor(dgrads if any(need_d) else None)
             _abi.check(lib.shine_sdf_bce_step(C.byref(od), C.byref(dd), _abi.ptr(coord), _abi.ptr(label),
                                               _abi.ptr(weight), n, sigma, scale, None, _abi.ptr(pred),
                                               _abi.ptr(loss), flags, stream), "shine_sdf_bce_step")
-            octree._reduce_replicas(od, dev)
             ctx.stash = (tgrads, dgrads)
         else:
             od = octree._descriptor(tables, None)
@@ -101,13 +100,12 @@ class _SdfBce(torch.autograd.Function):
             tables, dparams = params[:L], params[L:]
             tgrads = [torch.zeros_like(p) for p in tables]
             dgrads = [torch.zeros_like(p) if (p is not None and any(need_d)) else None for p in dparams]
-            od = octree._descriptor(tables, tgrads, n_points=n)
+            od = octree._descriptor(tables, tgrads)
             dd = decoder.c_descriptor(dgrads if any(need_d) else None)
             dl = dloss.detach().float().contiguous()
             _abi.check(_abi.lib().shine_sdf_bce_step(
                 C.byref(od), C.byref(dd), _abi.ptr(coord), _abi.ptr(label), _abi.ptr(weight), n, sigma, scale,
                 _abi.ptr(dl), None, None, flags, _abi.stream_ptr(coord.device)), "shine_sdf_bce_step")
-            octree._reduce_replicas(od, coord.device)
         out_t = [g if need else None for g, need in zip(tgrads, need_t)]
         out_d = [g if need else None for g, need in zip(dgrads, need_d)]
         return (None,) * 11 + tuple(out_t) + tuple(out_d)

@@ -97,14 +97,13 @@ class SdfTrainer:
         flags = (_abi.FLAG_REDUCTION_SUM if cfg.loss_reduction == "sum" else 0) | \
                 (_abi.FLAG_WEIGHTED if weighted else 0) | (_abi.FLAG_TF32X1 if self.tf32x1 else 0)
         scale = 1.0 if cfg.loss_reduction == "sum" else 1.0 / float(n_norm if n_norm else n)
-        od = self.octree._descriptor(None, self.table_grads, n_points=n)
+        od = self.octree._descriptor(None, self.table_grads)
         dd = self.decoder.c_descriptor(self.dec_grads if self._dec_trainable else None)
         self.loss.zero_()
         _abi.check(_abi.lib().shine_sdf_bce_step(
             C.byref(od), C.byref(dd), _abi.ptr(coord), _abi.ptr(sdf_label),
             _abi.ptr(weight) if weighted else None, n, float(self.sigma), scale, None,
             _abi.ptr(pred_out), _abi.ptr(self.loss), flags, _abi.stream_ptr(coord.device)), "shine_sdf_bce_step")
-        self.octree._reduce_replicas(od, coord.device)
         return self.loss
 
     def all_reduce_grads(self):

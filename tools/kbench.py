@@ -12,14 +12,17 @@ ap.add_argument("--n-azimuth", type=int, default=2048)
 ap.add_argument("--frames", type=int, default=1)
 ap.add_argument("--points", type=int, default=0)
 ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--leaf-vox", type=float, default=0.2)
+ap.add_argument("--step-m", type=float, default=2.0)
 ap.add_argument("--sorted", action="store_true", help="Morton-sort the batch (locality experiment)")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 from shine_mapping_b200 import Decoder, FeatureOctree, synth
 cfg = bench.workload_config(str(dev))
+cfg.leaf_vox_size = args.leaf_vox; cfg.calculate_world_scale()
 torch.manual_seed(42)
 octree, decoder = FeatureOctree(cfg), Decoder(cfg)
-pool = synth.build_scene_map(cfg, octree, n_azimuth=args.n_azimuth, n_frames=args.frames, frame_step_m=2.0, seed=42, device=str(dev))
+pool = synth.build_scene_map(cfg, octree, n_azimuth=args.n_azimuth, n_frames=args.frames, frame_step_m=args.step_m, seed=42, device=str(dev))
 n = args.points or len(pool)
 gen = torch.Generator(device=dev).manual_seed(1)
 coord, label, weight = pool.get_batch(n, gen)
@@ -27,7 +30,7 @@ if args.sorted:
     from shine_mapping_b200.feature_octree import points_to_morton, quantize_points
     order = torch.argsort(points_to_morton(quantize_points(coord, 12)))
     coord, label, weight = coord[order].contiguous(), label[order].contiguous(), weight[order].contiguous()
-print(f"N={n} rows={[int(p.shape[0]) for p in octree.hier_features]} pool={len(pool)}")
+print(f"table MB={sum(p.numel() for p in octree.hier_features)*4/1e6:.1f}", end=" "); print(f"N={n} rows={[int(p.shape[0]) for p in octree.hier_features]} pool={len(pool)}")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 def timeit(fn, name, bytes_per_pt=None):
