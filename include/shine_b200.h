@@ -137,6 +137,12 @@ typedef struct shine_adam_tensor {
 int shine_adam_step(const shine_adam_tensor* tensors, int32_t count, float beta1, float beta2, float eps,
                     int32_t step, int32_t zero_grad, void* stream);
 
+/* Same, CUDA-graph friendly: the step number lives on the device.  state = {int32 step, f32 bc1, f32 bc2_sqrt}
+ * (12 bytes, zero-initialised by the caller once); every call increments step and refreshes the bias
+ * corrections in a 1-thread kernel, then runs the Adam kernel reading them — so a captured graph can be replayed. */
+int shine_adam_step_dev(const shine_adam_tensor* tensors, int32_t count, float beta1, float beta2, float eps,
+                        void* state, int32_t zero_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,15 +52,51 @@ def save_checkpoint(octree, decoder, trainer, run_path, name, iters):
                os.path.join(run_path, f"{name}.pth"))
 
 
+class _GraphedIteration:
+    """One loop iteration {get_batch -> fused fwd+loss+bwd -> Adam(+zero grads)} captured as a CUDA graph: at
+    bs=4096 the iteration is launch-latency bound (5 small kernels), replaying a graph removes the host from the
+    loop.  Adam's step number lives on the device (`shine_adam_step_dev`); the graph is re-captured when the
+    learning rate changes (lr is a kernel parameter)."""
+
+    def __init__(self, trainer: SdfTrainer, pool, bs: int):
+        self.trainer, self.pool, self.bs = trainer, pool, bs
+        self.graph, self.lr = None, None
+
+    def _body(self):
+        coord, sdf_label, weight = self.pool.get_batch(self.bs)
+        self.trainer.forward_backward(coord, sdf_label, weight)
+        self.trainer.optimizer_step(zero_grad=True, device_step=True)
+
+    def run(self):
+        tr = self.trainer
+        if self.graph is None or self.lr != tr.lr:
+            dev = tr.flat_grad.device
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):     # warm-up outside capture (lazy inits, allocator)
+                self._body()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._body()
+            self.lr = tr.lr
+            return        # the warm-up call above already did this iteration's work once... and capture does not run
+        self.graph.replay()
+
+
 def run_shine_mapping_batch(config: SHINEConfig, octree: FeatureOctree, decoder: Decoder, pool, iters=None,
                             log_every: int = 0, run_path: str | None = None, process_group=None,
-                            shard_mode: str = "replicated"):
+                            shard_mode: str = "replicated", use_cuda_graph: bool | None = None):
     """-> dict(loss_first, loss_last, points_per_s, timing).  `octree` must already hold the map of `pool`."""
     check_supported(config)
     dev = octree.hier_features[0].device
     trainer = SdfTrainer(config, octree, decoder, process_group=process_group, shard_mode=shard_mode)
     world = torch.distributed.get_world_size(process_group) if torch.distributed.is_initialized() else 1
     iters = config.iters if iters is None else iters
+    if use_cuda_graph is None:
+        use_cuda_graph = world == 1
+    graphed = _GraphedIteration(trainer, pool, config.bs) if (use_cuda_graph and world == 1) else None
     trainer.zero_grad()
     losses = {}
     timing = {"load": 0.0, "step": 0.0}
@@ -69,10 +105,13 @@ def run_shine_mapping_batch(config: SHINEConfig, octree: FeatureOctree, decoder:
         if it == min(3, iters - 1):       # skip warm-up iterations in the throughput figure
             torch.cuda.synchronize(dev); t_begin = time.perf_counter(); it_begin = it
         step_lr_decay(trainer, config.lr, it, config.lr_decay_step, config.lr_iters_reduce_ratio)
-        coord, sdf_label, weight = pool.get_batch(config.bs)                       # shine_batch.py:115
-        trainer.forward_backward(coord, sdf_label, weight, n_norm=config.bs * world)   # :123-209
-        trainer.all_reduce_grads()
-        trainer.optimizer_step(zero_grad=True)                                      # :208-210
+        if graphed is not None:
+            graphed.run()
+        else:
+            coord, sdf_label, weight = pool.get_batch(config.bs)                       # shine_batch.py:115
+            trainer.forward_backward(coord, sdf_label, weight, n_norm=config.bs * world)   # :123-209
+            trainer.all_reduce_grads()
+            trainer.optimizer_step(zero_grad=True)                                      # :208-210
         if it == 0 or it == iters - 1 or (log_every and it % log_every == 0):
             losses[it] = float(trainer.loss)          # the only host read-back
         if run_path and ((it + 1) % config.save_freq_iters == 0) and it > 0:

@@ -937,12 +937,24 @@ struct AdamParams {
     int32_t count;
     float beta1, beta2, omb1, omb2, eps, bc1, bc2_sqrt;
     int32_t zero_grad;
+    const float* bc_dev;   // optional {bc1, bc2_sqrt} on the device (graph replay); overrides bc1 / bc2_sqrt
 };
+
+struct AdamDevState { int32_t step; float bc1, bc2_sqrt; };
+
+__global__ void adam_bump_kernel(AdamDevState* st, float beta1, float beta2) {
+    const int step = st->step + 1;
+    st->step = step;
+    st->bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+    st->bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+}
 
 __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamParams A) {
     const shine_adam_tensor& T = A.t[blockIdx.y];
     const int64_t n4 = T.numel >> 2;
-    const float step_size = T.lr / A.bc1;
+    const float bc1 = A.bc_dev ? A.bc_dev[0] : A.bc1;
+    const float bc2_sqrt = A.bc_dev ? A.bc_dev[1] : A.bc2_sqrt;
+    const float step_size = T.lr / bc1;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 p = reinterpret_cast<float4*>(T.param)[i];
         float4 gr = reinterpret_cast<float4*>(T.grad)[i];
@@ -955,7 +967,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamP
             if (T.weight_decay != 0.f) gk = fmaf(T.weight_decay, pp[k], gk);
             mm[k] = mm[k] + (gk - mm[k]) * A.omb1;                          // torch lerp_
             vv[k] = A.beta2 * vv[k] + A.omb2 * gk * gk;
-            const float denom = sqrtf(vv[k]) / A.bc2_sqrt + A.eps;
+            const float denom = sqrtf(vv[k]) / bc2_sqrt + A.eps;
             pp[k] -= step_size * (mm[k] / denom);
         }
         reinterpret_cast<float4*>(T.param)[i] = p;
@@ -971,7 +983,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamP
             const float m = T.exp_avg[i] + (gk - T.exp_avg[i]) * A.omb1;
             const float v = A.beta2 * T.exp_avg_sq[i] + A.omb2 * gk * gk;
             T.exp_avg[i] = m; T.exp_avg_sq[i] = v;
-            T.param[i] -= step_size * (m / (sqrtf(v) / A.bc2_sqrt + A.eps));
+            T.param[i] -= step_size * (m / (sqrtf(v) / bc2_sqrt + A.eps));
             if (A.zero_grad) T.grad[i] = 0.f;
         }
     }
@@ -1229,9 +1241,8 @@ int shine_reduce_grad_replicas(const shine_octree* oct, void* stream) {
     return (int)cudaGetLastError();
 }
 
-int shine_adam_step(const shine_adam_tensor* tensors, int32_t count, float beta1, float beta2, float eps, int32_t step,
-                    int32_t zero_grad, void* stream) {
-    if (!tensors || count < 1 || count > SHINE_ADAM_MAX_TENSORS || step < 1) return SHINE_ERR_INVALID_ARG;
+static int adam_launch(const shine_adam_tensor* tensors, int32_t count, float beta1, float beta2, float eps, int32_t step,
+                       const float* bc_dev, int32_t zero_grad, cudaStream_t st) {
     AdamParams A;
     int64_t max_n = 0;
     for (int i = 0; i < count; ++i) {
@@ -1242,7 +1253,7 @@ int shine_adam_step(const shine_adam_tensor* tensors, int32_t count, float beta1
         A.t[i] = t;
         if (t.numel > max_n) max_n = t.numel;
     }
-    A.count = count; A.beta1 = beta1; A.beta2 = beta2; A.eps = eps; A.zero_grad = zero_grad;
+    A.count = count; A.beta1 = beta1; A.beta2 = beta2; A.eps = eps; A.zero_grad = zero_grad; A.bc_dev = bc_dev;
     A.omb1 = (float)(1.0 - (double)beta1); A.omb2 = (float)(1.0 - (double)beta2);
     A.bc1 = (float)(1.0 - pow((double)beta1, (double)step));
     A.bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
@@ -1251,8 +1262,24 @@ int shine_adam_step(const shine_adam_tensor* tensors, int32_t count, float beta1
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     dim3 grid((unsigned)blocks, (unsigned)count);
-    adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A);
+    adam_kernel<<<grid, 256, 0, st>>>(A);
     return (int)cudaGetLastError();
+}
+
+int shine_adam_step(const shine_adam_tensor* tensors, int32_t count, float beta1, float beta2, float eps, int32_t step,
+                    int32_t zero_grad, void* stream) {
+    if (!tensors || count < 1 || count > SHINE_ADAM_MAX_TENSORS || step < 1) return SHINE_ERR_INVALID_ARG;
+    return adam_launch(tensors, count, beta1, beta2, eps, step, nullptr, zero_grad, (cudaStream_t)stream);
+}
+
+int shine_adam_step_dev(const shine_adam_tensor* tensors, int32_t count, float beta1, float beta2, float eps,
+                        void* state, int32_t zero_grad, void* stream) {
+    if (!tensors || count < 1 || count > SHINE_ADAM_MAX_TENSORS || !state) return SHINE_ERR_INVALID_ARG;
+    AdamDevState* st = reinterpret_cast<AdamDevState*>(state);
+    adam_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(st, beta1, beta2);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+    return adam_launch(tensors, count, beta1, beta2, eps, 1, &st->bc1, zero_grad, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -202,6 +202,7 @@ class FeatureOctree(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_dict_cache"] = None
+        state["_desc_cache"] = None
         state["_grad_scratch"] = {}
         state["_last_coord"] = None
         state["_hier_idx"] = []
@@ -380,6 +381,12 @@ class FeatureOctree(nn.Module):
             raise _abi.ShineB200Error("FeatureOctree is empty: call update() before querying")
         self._ensure_hash()
         tables = list(self.hier_features) if tables is None else list(tables)
+        # building the ctypes struct costs ~20 us of Python: reuse it while the same buffers are passed
+        sig = (tuple(t.data_ptr() for t in tables), tuple(g.data_ptr() if g is not None else 0 for g in grads)
+               if grads is not None else None, n_points, tuple(st.hash.data_ptr() for st in self._levels if st.hash is not None))
+        cached = getattr(self, "_desc_cache", None)
+        if cached is not None and cached[0] == sig:
+            return cached[1]
         d = _abi.ShineOctree()
         d.num_levels = self.featured_level_num
         d.feature_dim = self.feature_dim
@@ -403,6 +410,7 @@ class FeatureOctree(nn.Module):
                 r, buf = self._replicas_for(k, t.shape[0], n_points, t.device)
                 if r > 1:
                     lv.num_replicas, lv.grad_replicas = r, buf.data_ptr()
+        self._desc_cache = (sig, d)
         return d
 
     def _prep_coord(self, coord):

@@ -12,6 +12,7 @@ per-level lr scaled leaf -> coarse by lr_level_reduce_ratio).
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -35,6 +36,8 @@ class SdfTrainer:
             raise ValueError(shard_mode)
         self.config, self.octree, self.decoder = config, octree, decoder
         self.shard_mode = shard_mode
+        # gradient replicas for small hot levels (see FeatureOctree._replicas_for); on by default for big batches
+        self.use_replicas = os.environ.get("SHINE_FUSED_REPLICAS", "1") != "0"
         self.group = process_group
         self.tf32x1 = tf32x1
         self.lr = config.lr
@@ -68,6 +71,7 @@ class SdfTrainer:
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         self.step_count = 0   # fresh Adam state, like a rebuilt torch optimizer
+        self.adam_state = torch.zeros(3, dtype=torch.int32, device=dev)   # {step, bc1, bc2_sqrt} for graph replay
         views = []
         for p, o, s in zip(tables + dec, offs, sizes):
             views.append(self.flat_grad[o:o + s].view(p.shape) if p is not None else None)
@@ -87,7 +91,7 @@ class SdfTrainer:
 
     # ---- the hot path --------------------------------------------------------------------------------------
 
-    def forward_backward(self, coord, sdf_label, weight=None, n_norm=None, pred_out=None):
+    def forward_backward(self, coord, sdf_label, weight=None, n_norm=None, pred_out=None, accumulate_loss=False):
         """One fused launch: loss value (device scalar, accumulated into self.loss which is zeroed here) and
         gradients accumulated into the flat buffer.  Caller zeroes grads (zero_grad / fused in optimizer_step)."""
         self._sync()
@@ -97,13 +101,16 @@ class SdfTrainer:
         flags = (_abi.FLAG_REDUCTION_SUM if cfg.loss_reduction == "sum" else 0) | \
                 (_abi.FLAG_WEIGHTED if weighted else 0) | (_abi.FLAG_TF32X1 if self.tf32x1 else 0)
         scale = 1.0 if cfg.loss_reduction == "sum" else 1.0 / float(n_norm if n_norm else n)
-        od = self.octree._descriptor(None, self.table_grads)
+        od = self.octree._descriptor(None, self.table_grads, n_points=n if self.use_replicas else 0)
         dd = self.decoder.c_descriptor(self.dec_grads if self._dec_trainable else None)
-        self.loss.zero_()
+        if not accumulate_loss:
+            self.loss.zero_()
         _abi.check(_abi.lib().shine_sdf_bce_step(
             C.byref(od), C.byref(dd), _abi.ptr(coord), _abi.ptr(sdf_label),
             _abi.ptr(weight) if weighted else None, n, float(self.sigma), scale, None,
             _abi.ptr(pred_out), _abi.ptr(self.loss), flags, _abi.stream_ptr(coord.device)), "shine_sdf_bce_step")
+        if self.use_replicas:
+            self.octree._reduce_replicas(od, coord.device)
         return self.loss
 
     def all_reduce_grads(self):
@@ -115,8 +122,9 @@ class SdfTrainer:
             if buf.numel() and (self.shard_mode != "spatial" or self._dec_trainable):
                 torch.distributed.all_reduce(buf, group=self.group)
 
-    def optimizer_step(self, zero_grad: bool = True):
-        """Dense Adam with the reference's groups (utils/tools.py:57-83) as one multi-tensor launch."""
+    def optimizer_step(self, zero_grad: bool = True, device_step: bool = False):
+        """Dense Adam with the reference's groups (utils/tools.py:57-83) as one multi-tensor launch.  With
+        device_step the step number / bias corrections live on the device (CUDA-graph replayable)."""
         cfg = self.config
         tables, dec = self._params()
         self.step_count += 1
@@ -141,6 +149,11 @@ class SdfTrainer:
                 add(tables[k], k, lr_cur, 0.0)
             lr_cur *= cfg.lr_level_reduce_ratio
         arr = (_abi.ShineAdamTensor * len(entries))(*entries)
+        if device_step:
+            _abi.check(_abi.lib().shine_adam_step_dev(arr, len(entries), 0.9, 0.99, float(cfg.adam_eps),
+                                                      _abi.ptr(self.adam_state), 1 if zero_grad else 0,
+                                                      _abi.stream_ptr(tables[0].device)), "shine_adam_step_dev")
+            return
         _abi.check(_abi.lib().shine_adam_step(arr, len(entries), 0.9, 0.99, float(cfg.adam_eps), self.step_count,
                                               1 if zero_grad else 0, _abi.stream_ptr(tables[0].device)),
                    "shine_adam_step")
@@ -154,15 +167,39 @@ class SdfTrainer:
 
     # ---- host-buffer entry (the reference-facing call with HOST memory) -----------------------------------------
 
-    def step_from_host(self, coord_h, label_h, weight_h=None, optimizer: bool = False) -> float:
-        """coord/label(/weight) are pinned host tensors; copies them in, runs the fused step, reads the loss back."""
+    def step_from_host(self, coord_h, label_h, weight_h=None, optimizer: bool = False, chunks: int = 4) -> float:
+        """coord/label(/weight) are (pinned) host tensors.  The batch is cut into `chunks` slices: slice k+1 is copied
+        host->device on a copy stream while the fused kernel runs on slice k (gradients and the loss accumulate
+        across slices; the per-point scale uses the whole batch), then the loss is read back."""
         dev = self.flat_grad.device
-        coord = coord_h.to(dev, non_blocking=True)
-        label = label_h.to(dev, non_blocking=True)
-        weight = weight_h.to(dev, non_blocking=True) if weight_h is not None else None
+        n = coord_h.shape[0]
+        weighted = bool(self.config.loss_weight_on) and weight_h is not None
+        if getattr(self, "_h2d", None) is None or self._h2d[0].shape[0] < n:
+            self._h2d = (torch.empty(n, 3, device=dev), torch.empty(n, device=dev), torch.empty(n, device=dev))
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        coord_d, label_d, weight_d = (t[:n] for t in self._h2d)
+        main = torch.cuda.current_stream(dev)
+        chunks = max(1, min(chunks, (n + 65535) // 65536))
+        bounds = [(n * k // chunks, n * (k + 1) // chunks) for k in range(chunks)]
+        self._copy_stream.wait_stream(main)          # previous consumers of the staging buffers are done
+        events = []
+        with torch.cuda.stream(self._copy_stream):
+            for b, e in bounds:
+                coord_d[b:e].copy_(coord_h[b:e], non_blocking=True)
+                label_d[b:e].copy_(label_h[b:e], non_blocking=True)
+                if weighted:
+                    weight_d[b:e].copy_(weight_h[b:e], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+                events.append(ev)
         self.zero_grad()
-        loss = self.forward_backward(coord, label, weight)
+        self.loss.zero_()
+        for (b, e), ev in zip(bounds, events):
+            main.wait_event(ev)
+            if e > b:
+                self.forward_backward(coord_d[b:e], label_d[b:e], weight_d[b:e] if weighted else None, n_norm=n,
+                                      accumulate_loss=True)
         if optimizer:
             self.all_reduce_grads()
             self.optimizer_step(zero_grad=False)
-        return float(loss.item())
+        return float(self.loss.item())

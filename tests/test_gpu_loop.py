@@ -21,6 +21,14 @@ def test_batch_loop_trains_and_checkpoints(tmp_path, built_lib):
     pool = synth.build_scene_map(cfg, octree, n_azimuth=256, n_frames=2, seed=42, device=DEV)
     out = run_shine_mapping_batch(cfg, octree, decoder, pool, run_path=str(tmp_path))
     assert out["loss_last"] < 0.8 * out["loss_first"], out
+    print("graphed loop (incl. checkpoint write):", out["iters_per_s"], "it/s")
+    torch.manual_seed(42)
+    octree2, decoder2 = FeatureOctree(cfg), Decoder(cfg)
+    pool2 = synth.build_scene_map(cfg, octree2, n_azimuth=256, n_frames=2, seed=42, device=DEV)
+    out2 = run_shine_mapping_batch(cfg, octree2, decoder2, pool2, use_cuda_graph=False)
+    print("eager loop:", out2["iters_per_s"], "it/s")
+    assert out2["loss_last"] < 0.8 * out2["loss_first"], out2
+    assert abs(out["loss_last"] - out2["loss_last"]) < 0.1 * out2["loss_last"]   # same optimisation, different batches
     assert out["points_per_s"] > 1e6
     ck = torch.load(tmp_path / "model" / "model_iter_300.pth", weights_only=False)   # reference checkpoint layout
     assert set(ck) >= {"iters", "feature_octree", "geo_decoder", "optimizer"}
@@ -80,3 +88,19 @@ def test_two_gpu_data_parallel_matches_oracle(tmp_path, built_lib):
         assert np.abs(seg - g).max() <= 2e-4 * np.abs(g).max() + 1e-10, k
         off += (g.size + 3) & ~3
     assert abs(float(np.load(tmp_path / "loss.npy")) - want["loss"]) <= 2e-5 * abs(want["loss"])
+
+
+def test_step_from_host_matches_resident_step(built_lib):
+    """The host-buffer entry (pinned memory, chunked H2D overlapped with compute) gives the same loss / gradients
+    as one launch on resident inputs."""
+    from shine_mapping_b200 import SdfTrainer
+    case = make_case(n_points=3000, n_batch=300000, feat_levels=4, seed=61)
+    cfg, octree, dec = build_cuda_models(case, DEV)
+    coord_h = torch.from_numpy(case["coord"]).pin_memory(); label_h = torch.from_numpy(case["label"]).pin_memory()
+    tr = SdfTrainer(cfg, octree, dec)
+    loss_host = tr.step_from_host(coord_h, label_h, chunks=4)
+    g_host = tr.flat_grad.clone()
+    tr.zero_grad()
+    loss_res = float(tr.forward_backward(coord_h.to(DEV), label_h.to(DEV)))
+    assert abs(loss_host - loss_res) <= 2e-6 * abs(loss_res)
+    assert (g_host - tr.flat_grad).abs().max() <= 1e-4 * tr.flat_grad.abs().max()
