@@ -247,3 +247,36 @@ def train_step(octree: OracleOctree, dec: dict, coord, label, weight, sigma: flo
         "table_grads": [f.grad if f.grad is not None else torch.zeros_like(f) for f in octree.hier_features],
         "dec_grads": {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in dec.items()},
     }
+
+
+# --------------------------------------------------------------------------------------------------
+# continual-learning terms (BASELINE config 4): model/feature_octree.py:246-255, utils/incre_learning.py:8-40
+# --------------------------------------------------------------------------------------------------
+
+
+def cal_regularization(octree: OracleOctree, features_last_frame, importance_weight) -> torch.Tensor:
+    """FeatureOctree.cal_regularization (model/feature_octree.py:246-255): over the UNIQUE rows touched by the last
+    queried batch, sum Omega * (f - f_last)^2, per level."""
+    reg = torch.zeros(())
+    for i in range(octree.featured_level_num):
+        k = octree.featured_level_num - i - 1
+        u = octree.hierarchical_indices[i].flatten().unique()
+        diff = octree.hier_features[k][u] - features_last_frame[k][u]
+        reg = reg + (importance_weight[k][u] * diff ** 2).sum()
+    return reg
+
+
+def cal_feature_importance(octree: OracleOctree, dec: dict, coord_pool, label_pool, sigma, bs, down_rate=1,
+                           reduction="sum"):
+    """utils/incre_learning.py:8-40: sweep the pool in strides of bs*down_rate, accumulate |dL/dfeature| per row."""
+    importance = [torch.zeros_like(f) for f in octree.hier_features]
+    n = coord_pool.shape[0]
+    interval = bs * down_rate
+    for head in range(0, n, interval):
+        c = coord_pool[head:min(head + interval, n):down_rate]
+        l = label_pool[head:min(head + interval, n):down_rate]
+        res = train_step(octree, dec, c, l, None, sigma, False, reduction)
+        for k, g in enumerate(res["table_grads"]):
+            importance[k] += g.abs()
+            importance[k][-1] *= 0
+    return importance

@@ -104,3 +104,67 @@ def test_step_from_host_matches_resident_step(built_lib):
     loss_res = float(tr.forward_backward(coord_h.to(DEV), label_h.to(DEV)))
     assert abs(loss_host - loss_res) <= 2e-6 * abs(loss_res)
     assert (g_host - tr.flat_grad).abs().max() <= 1e-4 * tr.flat_grad.abs().max()
+
+
+def test_regularization_and_importance_match_oracle(built_lib):
+    """BASELINE config 4 terms: cal_regularization (value + gradient) and cal_feature_importance vs the oracle."""
+    from oracle import shine_oracle as orc
+    from shine_mapping_b200 import SdfTrainer
+    from shine_mapping_b200.incre_loop import add_regularization, cal_feature_importance
+    from tests.parity_utils import oracle_from_case
+    case = make_case(n_points=2000, n_batch=3000, feat_levels=3, seed=71, reduction="sum")
+    cfg, octree, dec = build_cuda_models(case, DEV)
+    g = torch.Generator().manual_seed(5)
+    last = [t + 0.01 * torch.randn(t.shape, generator=g).numpy() for t in case["tables"]]
+    imp = [torch.rand(t.shape, generator=g).numpy() for t in case["tables"]]
+    octree.features_last_frame = [torch.from_numpy(np.asarray(t, dtype=np.float32)).to(DEV) for t in last]
+    octree.importance_weight = [torch.from_numpy(np.asarray(t, dtype=np.float32)).to(DEV) for t in imp]
+    coord = torch.from_numpy(case["coord"]).to(DEV); label = torch.from_numpy(case["label"]).to(DEV)
+    tr = SdfTrainer(cfg, octree, dec)
+    # regulariser alone: value + gradient
+    tr.zero_grad()
+    octree.query_feature(coord)
+    lam = 1e3
+    reg = add_regularization(tr, octree, lam)
+    assert abs(float(reg) - float(octree.cal_regularization())) <= 1e-5 * abs(float(reg))
+    o, odec = oracle_from_case(case)
+    o.get_indices(torch.from_numpy(case["coord"]))
+    flast = [torch.from_numpy(np.asarray(t, dtype=np.float32)) for t in last]
+    fimp = [torch.from_numpy(np.asarray(t, dtype=np.float32)) for t in imp]
+    want = orc.cal_regularization(o, flast, fimp)
+    (lam * want).backward()
+    assert abs(float(reg) - float(want)) <= 1e-5 * abs(float(want))
+    for k, f in enumerate(o.hier_features):
+        got = tr.table_grads[k].cpu().numpy()
+        assert np.abs(got - f.grad.numpy()).max() <= 1e-5 * np.abs(f.grad.numpy()).max() + 1e-12
+    # importance sweep
+    octree.importance_weight = [torch.zeros_like(p) for p in octree.hier_features]
+    cal_feature_importance(tr, octree, coord, label, bs=512, down_rate=2)
+    o2, odec2 = oracle_from_case(case)
+    want_imp = orc.cal_feature_importance(o2, odec2, torch.from_numpy(case["coord"]), torch.from_numpy(case["label"]),
+                                          case["cfg"]["sigma"], 512, 2, "sum")
+    for k in range(3):
+        got = octree.importance_weight[k].cpu().numpy()
+        assert np.abs(got - want_imp[k].numpy())[:-1].max() <= 2e-4 * np.abs(want_imp[k].numpy()).max() + 1e-10
+
+
+def test_incremental_loop_runs(built_lib):
+    from shine_mapping_b200 import Decoder, FeatureOctree, synth
+    from shine_mapping_b200.incre_loop import run_shine_mapping_incremental
+    cfg = make_config(3, device=DEV, bs=2048, lr=0.01, iters=40, continual_learning_reg=True, lambda_forget=1e3,
+                      freeze_after_frame=2)
+    torch.manual_seed(1)
+    octree, decoder = FeatureOctree(cfg), Decoder(cfg)
+    dirs, boxes = synth.lidar_directions(128, device=DEV), synth.default_boxes(DEV)
+    gen = torch.Generator(device=DEV).manual_seed(3)
+    frames = []
+    for f in range(3):
+        origin = torch.tensor([2.0 * f, 0.0, 0.0], device=DEV)
+        hits = synth.raycast_scene(origin, dirs, boxes, cfg.min_range, cfg.pc_radius)
+        frames.append(synth.sample_rays(hits * cfg.scale, origin * cfg.scale, cfg, gen))
+    hist = run_shine_mapping_incremental(cfg, octree, decoder, frames)
+    assert len(hist) == 3 and all(h["bce_last"] < h["bce_first"] for h in hist), hist
+    assert all(np.isfinite(h["loss_last"]) for h in hist)
+    assert hist[2]["rows"][-1] > hist[0]["rows"][-1]                       # the map grew
+    assert not any(p.requires_grad for p in decoder.parameters())          # frozen after frame 2
+    assert all(w.abs().sum() > 0 for w in octree.importance_weight)
