@@ -19,6 +19,7 @@ ADAM_MAX_TENSORS = 16
 FLAG_REDUCTION_SUM = 1
 FLAG_WEIGHTED = 2
 FLAG_TF32X1 = 4
+FLAG_TCGEN05 = 8
 
 
 class ShineLevel(C.Structure):

@@ -58,7 +58,7 @@ struct __align__(64) HashSlot {
     unsigned long long key;   // Morton code of the voxel, kEmptyKey when free
     int32_t node;             // insertion ordinal (diagnostics)
     int32_t pad[5];
-    int32_t ids[8];           // rows of the 8 corners in the level's feature table (second 32-B sector)
+    int32_t ids[8];           // rows of the 8 corners, stored z-bit-major: [c0 c2 c4 c6 | c1 c3 c5 c7] (second sector)
 };
 static_assert(sizeof(HashSlot) == SHINE_HASH_SLOT_BYTES, "slot must be 64 bytes");
 
@@ -188,7 +188,7 @@ __global__ void hash_insert_kernel(HashSlot* __restrict__ slots, uint32_t mask, 
         if (prev == kEmptyKey || prev == key) {
             slots[h].node = node_base + (int32_t)i;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) slots[h].ids[c] = corner_ids[i * 8 + c];
+            for (int c = 0; c < 8; ++c) slots[h].ids[(c >> 1) + 4 * (c & 1)] = corner_ids[i * 8 + c];
             return;
         }
         h = (h + 1) & mask;
@@ -220,9 +220,9 @@ __global__ void get_indices_kernel(const __grid_constant__ shine_octree oct, con
 #pragma unroll
         for (int c = 0; c < 4; ++c) dst[c] = make_longlong2(-1, -1);
     } else {
-        const int4 a = ldg_i4(slots[s].ids), b = ldg_i4(slots[s].ids + 4);
-        dst[0] = make_longlong2(a.x, a.y); dst[1] = make_longlong2(a.z, a.w);
-        dst[2] = make_longlong2(b.x, b.y); dst[3] = make_longlong2(b.z, b.w);
+        const int4 a = ldg_i4(slots[s].ids), b = ldg_i4(slots[s].ids + 4);   // a: even corners, b: odd corners
+        dst[0] = make_longlong2(a.x, b.x); dst[1] = make_longlong2(a.y, b.y);
+        dst[2] = make_longlong2(a.z, b.z); dst[3] = make_longlong2(a.w, b.w);
     }
 }
 
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256) query_fwd_kernel(const __grid_constant__ 
         const int s = probe_slot(slots, lv.hash_capacity - 1, morton_of(x, y, z, lv.level));
         if (s < 0) continue;
         const int4 ia = ldg_i4(slots[s].ids), ib = ldg_i4(slots[s].ids + 4);
-        const int ids[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
+        const int ids[8] = {ia.x, ib.x, ia.y, ib.y, ia.z, ib.z, ia.w, ib.w};   // un-permute (z-bit-major storage)
         float4 v[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) v[c] = ldg_f4(lv.features + (int64_t)ids[c] * F + 4 * part);
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256) query_bwd_kernel(const __grid_constant__ 
         const int s = probe_slot(slots, lv.hash_capacity - 1, morton_of(x, y, z, lv.level));
         if (s < 0) continue;
         const int4 ia = ldg_i4(slots[s].ids), ib = ldg_i4(slots[s].ids + 4);
-        const int ids[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
+        const int ids[8] = {ia.x, ib.x, ia.y, ib.y, ia.z, ib.z, ia.w, ib.w};   // un-permute (z-bit-major storage)
         Blend b; b.init(x, y, z, lv.level, oct.poly_interp != 0);
         float* gb = grad_base(lv, (uint32_t)(gtid >> 5), F) + 4 * part;
 #pragma unroll
@@ -593,7 +593,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         }
 
         // ---- 8-corner gather + blend, summed over levels (model/feature_octree.py:222-234).  The pair splits the
-        //      CORNERS: lane `half` fetches corners 4*half..4*half+3 as whole 32-byte rows (one LDG.256 each) and
+        //      CORNERS: lane `half` fetches the corners with z bit == half as whole 32-byte rows (one LDG.256 each) and
         //      blends all 8 channels; the two partial sums are then exchanged so that each lane ends with the 4
         //      channels of its row-half. ----
         float feat[4];
@@ -604,6 +604,9 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                 if (i < L && slot[i] >= 0) {
                     const shine_level& lv = P.oct.lv[i];
                     const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
+                    // lane `half` takes the corners whose z bit is `half` (c = 2k + half): in every load instruction the
+                    // two lanes of a pair then fetch z-neighbours, whose rows are consecutive in the table (lexicographic
+                    // numbering) and usually share a 128-byte line -> one L1TEX wavefront instead of two
                     const int4 id4 = ldg_i4(slots[slot[i]].ids + 4 * half);
                     float r0[8], r1[8], r2[8], r3[8];
                     ldg_row8(lv.features + (int64_t)id4.x * kF, r0);
@@ -611,10 +614,9 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                     ldg_row8(lv.features + (int64_t)id4.z * kF, r2);
                     ldg_row8(lv.features + (int64_t)id4.w * kF, r3);
                     Blend b; b.init(x, y, z, lv.level, poly);
-                    const float wx = half ? b.tx : b.ux;            // corner bit 2 (x) is this lane's `half`
-                    const float wxy0 = __fmul_rn(wx, b.uy), wxy1 = __fmul_rn(wx, b.ty);
-                    const float w0 = __fmul_rn(wxy0, b.uz), w1 = __fmul_rn(wxy0, b.tz);
-                    const float w2 = __fmul_rn(wxy1, b.uz), w3 = __fmul_rn(wxy1, b.tz);
+                    const float wz = half ? b.tz : b.uz;
+                    const float w0 = __fmul_rn(__fmul_rn(b.ux, b.uy), wz), w1 = __fmul_rn(__fmul_rn(b.ux, b.ty), wz);
+                    const float w2 = __fmul_rn(__fmul_rn(b.tx, b.uy), wz), w3 = __fmul_rn(__fmul_rn(b.tx, b.ty), wz);
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         float a = acc[q];
@@ -828,7 +830,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                 const shine_level& lv = P.oct.lv[i];
                 const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
                 const int4 ia = ldg_i4(slots[slot[i]].ids), ib = ldg_i4(slots[slot[i]].ids + 4);
-                const int ids[8] = {ia.x, ia.y, ia.z, ia.w, ib.x, ib.y, ib.z, ib.w};
+                const int ids[8] = {ia.x, ib.x, ia.y, ib.y, ia.z, ib.z, ia.w, ib.w};   // un-permute (z-bit-major storage)
                 Blend b; b.init(x, y, z, lv.level, poly);
                 float* gb = grad_base(lv, (uint32_t)tile, kF) + 4 * half;
 #pragma unroll
@@ -903,6 +905,252 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(smu[SmemPlan::B3 + 1]) : "memory");
         }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// tcgen05 inference kernel (SHINE_FLAG_TCGEN05): query_feature -> Decoder.sdf with the decoder on the 5th-gen
+// tensor cores.  One thread per point: it walks the hash, gathers its 8 x L rows with 256-bit loads and blends all
+// 8 channels, then the block's 128 feature vectors become the A operand (M = 128 points) of
+//     D1[128x32] = X[128x8] * W1^T      (tcgen05.mma kind::tf32, 3xTF32: hi*hi + lo*hi + hi*lo)
+//     D2[128x32] = relu(D1+b1)[128x32] * W2^T
+// with operands in shared memory (canonical K-major, no swizzle: 8-row x 16-byte core matrices, LBO = 128 B between
+// the two K-chunks of one MMA, SBO = stride of an 8-row group) and accumulators in Tensor Memory; every thread reads
+// its own row of D back with tcgen05.ld (TMEM lane = point) for bias / ReLU / the 32->1 output layer.
+// ------------------------------------------------------------------------------------------------------
+
+struct TcPlan {                                   // byte offsets in dynamic shared memory
+    static constexpr int A2H = 0;                 // H1  hi  [16 groups][8 chunks][8 rows][16 B]   = 16 KB
+    static constexpr int A2L = A2H + 16384;
+    static constexpr int A1H = A2H;               // X   hi  [16 groups][2 chunks][8 rows][16 B]   = 4 KB; aliases the
+    static constexpr int A1L = A2H + 4096;        //     H1 tile: X is dead once layer 1's MMAs have completed
+    static constexpr int W1H = A2L + 16384;       // W1  hi  [4 groups][2 chunks][8][16 B]         = 1 KB
+    static constexpr int W1L = W1H + 1024;
+    static constexpr int W2H = W1L + 1024;        // W2  hi  [4 groups][8 chunks][8][16 B]         = 4 KB
+    static constexpr int W2L = W2H + 4096;
+    static constexpr int VEC = W2L + 4096;        // b1[32] b2[32] w3[32] b3 (floats)
+    static constexpr int BAR = VEC + 100 * 4;     // mbarrier (8 B), tmem base (4 B)
+    static constexpr int BYTES = BAR + 16;
+};
+
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);      // version 1 (Blackwell), SWIZZLE_NONE
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
+        ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (int spin = 0; !done; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1 << 22)) __trap();   // never hang the GPU on a protocol bug
+    }
+}
+
+template <int LMAX>
+__global__ void __launch_bounds__(128, 5) sdf_infer_tc_kernel(const __grid_constant__ StepParams P) {
+    extern __shared__ __align__(128) unsigned char tsm[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(tsm);
+    float* vec = reinterpret_cast<float*>(tsm + TcPlan::VEC);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tsm + TcPlan::BAR + 8);
+    const uint32_t bar = sbase + TcPlan::BAR;
+
+    // ---- prologue: weights (hi/lo) into the canonical UMMA layout, TMEM allocation, mbarrier -------------------
+    for (int i = tid; i < kH * kF; i += 128) {
+        const int n = i / kF, k = i % kF;
+        uint32_t hi, lo; split_tf32(P.dec.w1[i], hi, lo);
+        const int off = (n >> 3) * 256 + (k >> 2) * 128 + (n & 7) * 16 + (k & 3) * 4;
+        *reinterpret_cast<uint32_t*>(tsm + TcPlan::W1H + off) = hi;
+        *reinterpret_cast<uint32_t*>(tsm + TcPlan::W1L + off) = lo;
+    }
+    for (int i = tid; i < kH * kH; i += 128) {
+        const int n = i / kH, k = i % kH;
+        uint32_t hi, lo; split_tf32(P.dec.w2[i], hi, lo);
+        const int off = (n >> 3) * 1024 + (k >> 2) * 128 + (n & 7) * 16 + (k & 3) * 4;
+        *reinterpret_cast<uint32_t*>(tsm + TcPlan::W2H + off) = hi;
+        *reinterpret_cast<uint32_t*>(tsm + TcPlan::W2L + off) = lo;
+    }
+    if (tid < kH) {
+        vec[tid] = P.dec.b1 ? P.dec.b1[tid] : 0.f;
+        vec[32 + tid] = P.dec.b2 ? P.dec.b2[tid] : 0.f;
+        vec[64 + tid] = P.dec.w3[tid];
+    }
+    if (tid == 0) {
+        vec[96] = P.dec.b3 ? P.dec.b3[0] : 0.f;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(sbase + TcPlan::BAR + 8) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t trow = tmem + ((uint32_t)(32 * warp) << 16);          // this warp's 32 TMEM lanes
+    // instruction descriptor: D=F32, A=B=TF32, both K-major, N=32 (>>3), M=128 (>>4)
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+
+    const bool poly = P.oct.poly_interp != 0;
+    const int L = P.oct.num_levels;
+    bool consecutive = true;
+#pragma unroll
+    for (int i = 1; i < LMAX; ++i)
+        if (i < L && P.oct.lv[i].level != P.oct.lv[0].level - i) consecutive = false;
+    uint32_t phase = 0;
+    const int rg = tid >> 3, r0 = tid & 7;                                   // 8-row group / row within it
+    const int num_tiles = (int)((P.n + 127) / 128);
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int64_t p = (int64_t)tile * 128 + tid;
+        const bool valid = p < P.n;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (valid) { x = __ldg(P.coord + 3 * p); y = __ldg(P.coord + 3 * p + 1); z = __ldg(P.coord + 3 * p + 2); }
+
+        // ---- hash walk + gather + blend: one thread does the whole point --------------------------------------
+        float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        bool present = false;
+        {
+            const unsigned long long key0 = valid ? morton_of(x, y, z, P.oct.lv[0].level) : 0ull;
+            int slot[LMAX];
+            unsigned long long kq[LMAX], kf[LMAX];
+#pragma unroll
+            for (int i = 0; i < LMAX; ++i) {          // first-probe keys of every level in flight together
+                slot[i] = -1;
+                if (i < L && valid) {
+                    const shine_level& lv = P.oct.lv[i];
+                    kq[i] = consecutive ? (key0 >> (3 * i)) : morton_of(x, y, z, lv.level);
+                    slot[i] = (int)(hash_key(kq[i]) & (lv.hash_capacity - 1));
+                    kf[i] = __ldg(&reinterpret_cast<const HashSlot*>(lv.hash_slots)[slot[i]].key);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < LMAX; ++i) {
+                if (i < L && valid && kf[i] != kq[i]) {
+                    if (kf[i] == kEmptyKey) slot[i] = -1;
+                    else {
+                        const shine_level& lv = P.oct.lv[i];
+                        slot[i] = probe_slot_from(reinterpret_cast<const HashSlot*>(lv.hash_slots), lv.hash_capacity - 1,
+                                                  kq[i], (uint32_t)slot[i] + 1);
+                    }
+                }
+                if (i == P.mask_level) present = slot[i] >= 0;
+            }
+#pragma unroll
+            for (int i = 0; i < LMAX; ++i) {
+                if (i < L && slot[i] >= 0) {
+                    const shine_level& lv = P.oct.lv[i];
+                    const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
+                    Blend b; b.init(x, y, z, lv.level, poly);
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {                       // corners hh, 2+hh, 4+hh, 6+hh
+                        const int4 id4 = ldg_i4(slots[slot[i]].ids + 4 * hh);
+                        float q0[8], q1[8], q2[8], q3[8];
+                        ldg_row8(lv.features + (int64_t)id4.x * kF, q0);
+                        ldg_row8(lv.features + (int64_t)id4.y * kF, q1);
+                        ldg_row8(lv.features + (int64_t)id4.z * kF, q2);
+                        ldg_row8(lv.features + (int64_t)id4.w * kF, q3);
+                        const float w0 = b.w(hh), w1 = b.w(2 + hh), w2 = b.w(4 + hh), w3 = b.w(6 + hh);   // z-bit-major ids
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float a = f[q];
+                            a = fmaf(w0, q0[q], a); a = fmaf(w1, q1[q], a); a = fmaf(w2, q2[q], a); a = fmaf(w3, q3[q], a);
+                            f[q] = a;
+                        }
+                    }
+                }
+            }
+        }
+        if (P.mask && valid) P.mask[p] = (uint8_t)present;
+
+        // ---- layer 1 on the tensor core ----------------------------------------------------------------------------
+        {
+            uint32_t h[8], l[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) split_fast(f[q], h[q], l[q]);
+            const int off = rg * 256 + r0 * 16;
+            *reinterpret_cast<uint4*>(tsm + TcPlan::A1H + off) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(tsm + TcPlan::A1H + off + 128) = make_uint4(h[4], h[5], h[6], h[7]);
+            *reinterpret_cast<uint4*>(tsm + TcPlan::A1L + off) = make_uint4(l[0], l[1], l[2], l[3]);
+            *reinterpret_cast<uint4*>(tsm + TcPlan::A1L + off + 128) = make_uint4(l[4], l[5], l[6], l[7]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t ah = umma_desc(sbase + TcPlan::A1H, 128, 256), al = umma_desc(sbase + TcPlan::A1L, 128, 256);
+            const uint64_t bh = umma_desc(sbase + TcPlan::W1H, 128, 256), bl = umma_desc(sbase + TcPlan::W1L, 128, 256);
+            umma_tf32(tmem, al, bh, idesc, 0u);
+            umma_tf32(tmem, ah, bl, idesc, 1u);
+            umma_tf32(tmem, ah, bh, idesc, 1u);
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+        }
+        mbar_wait(bar, phase); phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        float hv[32];
+        tmem_ld32(trow, hv);
+        tmem_wait_ld();
+
+        // ---- bias + ReLU, layer 2 ------------------------------------------------------------------------------
+        {
+            const int off = rg * 1024 + r0 * 16;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 bb = *reinterpret_cast<const float4*>(vec + 4 * c);
+                uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                split_fast(fmaxf(hv[4 * c + 0] + bb.x, 0.f), h0, l0); split_fast(fmaxf(hv[4 * c + 1] + bb.y, 0.f), h1, l1);
+                split_fast(fmaxf(hv[4 * c + 2] + bb.z, 0.f), h2, l2); split_fast(fmaxf(hv[4 * c + 3] + bb.w, 0.f), h3, l3);
+                *reinterpret_cast<uint4*>(tsm + TcPlan::A2H + off + 128 * c) = make_uint4(h0, h1, h2, h3);
+                *reinterpret_cast<uint4*>(tsm + TcPlan::A2L + off + 128 * c) = make_uint4(l0, l1, l2, l3);
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t ah = umma_desc(sbase + TcPlan::A2H + 256 * kk, 128, 1024), al = umma_desc(sbase + TcPlan::A2L + 256 * kk, 128, 1024);
+                const uint64_t bh = umma_desc(sbase + TcPlan::W2H + 256 * kk, 128, 1024), bl = umma_desc(sbase + TcPlan::W2L + 256 * kk, 128, 1024);
+                umma_tf32(tmem + 32, al, bh, idesc, kk > 0 ? 1u : 0u);
+                umma_tf32(tmem + 32, ah, bl, idesc, 1u);
+                umma_tf32(tmem + 32, ah, bh, idesc, 1u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+        }
+        mbar_wait(bar, phase); phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem_ld32(trow + 32, hv);
+        tmem_wait_ld();
+
+        // ---- bias + ReLU + 32 -> 1 output layer ----------------------------------------------------------------------
+        float pr = vec[96];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float4 bb = *reinterpret_cast<const float4*>(vec + 32 + 4 * c);
+            const float4 ww = *reinterpret_cast<const float4*>(vec + 64 + 4 * c);
+            pr = fmaf(fmaxf(hv[4 * c + 0] + bb.x, 0.f), ww.x, pr); pr = fmaf(fmaxf(hv[4 * c + 1] + bb.y, 0.f), ww.y, pr);
+            pr = fmaf(fmaxf(hv[4 * c + 2] + bb.z, 0.f), ww.z, pr); pr = fmaf(fmaxf(hv[4 * c + 3] + bb.w, 0.f), ww.w, pr);
+        }
+        if (valid) P.pred[p] = pr;
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tmem) : "memory");
     }
 }
 
@@ -1073,6 +1321,35 @@ int launch_fused(const StepParams& P, uint32_t flags, cudaStream_t st) {
     return small ? launch_fused_t<3, TRAIN, DEC_GRAD, 4>(P, st) : launch_fused_t<3, TRAIN, DEC_GRAD, 8>(P, st);
 }
 
+template <int LMAX>
+int launch_infer_tc_t(const StepParams& P, cudaStream_t st) {
+    auto kern = sdf_infer_tc_kernel<LMAX>;
+    static int per_sm_cached = 0;
+    if (per_sm_cached == 0) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcPlan::BYTES);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return (int)e;
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, kern);
+        if (e != cudaSuccess) return (int)e;
+        const int by_regs = fa.numRegs > 0 ? 65536 / (fa.numRegs * 128) : 1;
+        const int by_smem = (227 * 1024) / (TcPlan::BYTES + 1024);
+        int q = by_regs < by_smem ? by_regs : by_smem;
+        if (q > 8) q = 8;                      // 8 x 64 TMEM columns = all 512
+        per_sm_cached = q < 1 ? 1 : q;
+    }
+    const int tiles = (int)((P.n + 127) / 128);
+    int grid = sm_count() * per_sm_cached;
+    if (grid > tiles) grid = tiles;
+    if (grid < 1) grid = 1;
+    kern<<<grid, 128, TcPlan::BYTES, st>>>(P);
+    return (int)cudaGetLastError();
+}
+int launch_infer_tc(const StepParams& P, cudaStream_t st) {
+    return P.oct.num_levels <= 4 ? launch_infer_tc_t<4>(P, st) : launch_infer_tc_t<8>(P, st);
+}
+
 int fill_params(StepParams& P, const shine_octree* oct, const shine_decoder* dec, const float* coord, int64_t n) {
     if (n < 0 || (n > 0 && !coord)) return SHINE_ERR_INVALID_ARG;
     if (n > (int64_t)INT32_MAX * 8) return SHINE_ERR_UNSUPPORTED;
@@ -1179,6 +1456,7 @@ int shine_sdf_infer(const shine_octree* oct, const shine_decoder* dec, const flo
     if (rc) return rc;
     if (n == 0) return SHINE_OK;
     P.pred = out_pred; P.mask = out_mask; P.mask_level = mask_level;
+    if (flags & SHINE_FLAG_TCGEN05) return launch_infer_tc(P, (cudaStream_t)stream);
     return launch_fused<false, false>(P, flags, (cudaStream_t)stream);
 }
 

@@ -102,6 +102,22 @@ def test_infer_and_mask_match_step_pred():
         assert np.array_equal(mask.cpu().numpy(), (want["indices"][lvl] >= 0).all(1))
 
 
+@pytest.mark.parametrize("levels,n_batch", [(4, 3000), (2, 100), (3, 40000)])
+def test_tcgen05_infer_matches_oracle(levels, n_batch):
+    """tcgen05.mma / TMEM decoder (SHINE_FLAG_TCGEN05) vs the oracle and vs the mma.sync kernel, incl. the mask."""
+    from shine_mapping_b200 import sdf_infer
+    case = make_case(n_points=2500, n_batch=n_batch, feat_levels=levels, seed=90 + levels)
+    cfg, octree, dec = build_cuda_models(case, DEV)
+    coord = torch.from_numpy(case["coord"]).to(DEV)
+    want = run_oracle_step(case)
+    pred, mask = sdf_infer(octree, dec, coord, mask_level=0, tcgen05=True)
+    torch.cuda.synchronize()
+    assert np.abs(pred.cpu().numpy() - want["pred"]).max() < 2e-5
+    assert np.array_equal(mask.cpu().numpy(), (want["indices"][0] >= 0).all(1))
+    ref = sdf_infer(octree, dec, coord)
+    assert (pred - ref).abs().max() < 1e-5
+
+
 def test_points_to_morton_bit_exact():
     from shine_mapping_b200 import _abi
     from oracle import shine_oracle as orc

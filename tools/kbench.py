@@ -52,6 +52,7 @@ timeit(lambda: trf3.forward_backward(coord, label), "step 3xTF32 frozen decoder"
 timeit(lambda: trf1.forward_backward(coord, label), "step 1xTF32 frozen decoder")
 timeit(lambda: sdf_infer(octree, decoder, coord), "infer 3xTF32")
 timeit(lambda: sdf_infer(octree, decoder, coord, tf32x1=True), "infer 1xTF32")
+timeit(lambda: sdf_infer(octree, decoder, coord, tcgen05=True), "infer tcgen05 3xTF32")
 feat = torch.empty(n, 8, device=dev); od = octree._descriptor(None, tr3.table_grads, n_points=n)
 lib = _abi.lib(); st = _abi.stream_ptr(dev)
 timeit(lambda: lib.shine_query_fwd(C.byref(od), _abi.ptr(coord), n, _abi.ptr(feat), st), "query_fwd (gather only)")
