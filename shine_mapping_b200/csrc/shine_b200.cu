@@ -468,19 +468,28 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
     }
     if (tid == 0) smem[SmemPlan::B3] = P.dec.b3 ? P.dec.b3[0] : 0.f;
     if (DEC_GRAD) for (int i = tid; i < 1380; i += blockDim.x) smem[SmemPlan::RED + i] = 0.f;
-    uint32_t tacc = 0;   // this warp's TMEM parking area
-    if (DEC_GRAD) {
-        if (warp == 0) {   // one warp allocates 128 columns for the block (2 blocks/SM -> 256 of 512)
+    // Tensor-Memory parking areas of this warp (lanes 32*(warp&3).., column group warp>>2):
+    //   tpark: per-tile state that must survive the MLP phase (blend factors tx,ty,tz of every level + slot indices)
+    //   tacc : decoder-gradient accumulators (DEC_GRAD only)
+    constexpr int kPark = LMAX <= 4 ? 16 : 32;                           // floats parked per lane
+    constexpr int kColsPerGroup = DEC_GRAD ? 128 : kPark;                // 56 acc (+pad to 64) + park
+    constexpr int kTmemCols = TRAIN ? 2 * kColsPerGroup : 0;             // 256 (dec grads) / 32 / 64, power of two
+    uint32_t tacc = 0, tpark = 0;
+    if (TRAIN) {
+        if (warp == 0) {   // one warp allocates for the block (2 blocks/SM x 256 columns = the SM's 512)
             const uint32_t sa = (uint32_t)__cvta_generic_to_shared(smu + SmemPlan::B3 + 1);
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(sa) : "memory");
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sa), "n"(kTmemCols > 0 ? kTmemCols : 32) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
     __syncthreads();
-    if (DEC_GRAD) {
+    if (TRAIN) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        tacc = smu[SmemPlan::B3 + 1] + ((uint32_t)(32 * (warp & 3)) << 16) + 64u * (uint32_t)(warp >> 2);
+        tacc = smu[SmemPlan::B3 + 1] + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)kColsPerGroup * (uint32_t)(warp >> 2);
+        tpark = tacc + (DEC_GRAD ? 64u : 0u);
+    }
+    if (DEC_GRAD) {
         SHINE_ACC_DECL;
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
@@ -597,8 +606,11 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         //      blends all 8 channels; the two partial sums are then exchanged so that each lane ends with the 4
         //      channels of its row-half. ----
         float feat[4];
+        float pk[kPark];   // [3i..3i+2] = tx,ty,tz of level i; [3*LMAX + i] = slot index (parked in TMEM over the MLP)
         {
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < kPark; ++i) pk[i] = 0.f;
 #pragma unroll
             for (int i = 0; i < LMAX; ++i) {
                 if (i < L && slot[i] >= 0) {
@@ -614,6 +626,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                     ldg_row8(lv.features + (int64_t)id4.z * kF, r2);
                     ldg_row8(lv.features + (int64_t)id4.w * kF, r3);
                     Blend b; b.init(x, y, z, lv.level, poly);
+                    pk[3 * i] = b.tx; pk[3 * i + 1] = b.ty; pk[3 * i + 2] = b.tz;
                     const float wz = half ? b.tz : b.uz;
                     const float w0 = __fmul_rn(__fmul_rn(b.ux, b.uy), wz), w1 = __fmul_rn(__fmul_rn(b.ux, b.ty), wz);
                     const float w2 = __fmul_rn(__fmul_rn(b.tx, b.uy), wz), w3 = __fmul_rn(__fmul_rn(b.tx, b.ty), wz);
@@ -631,6 +644,12 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                 const float recv = __shfl_xor_sync(kFull, send, 2);
                 feat[q] = (half ? acc[4 + q] : acc[q]) + recv;
             }
+        }
+        if (TRAIN) {
+#pragma unroll
+            for (int i = 0; i < LMAX; ++i) pk[3 * LMAX + i] = __int_as_float(slot[i]);
+            if (kPark == 16) tmem_st16(tpark, pk); else tmem_st32(tpark, pk);
+            tmem_wait_st();
         }
         if (!TRAIN && P.mask) {
             bool present = false;
@@ -710,12 +729,14 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         // ---- sdf_bce_loss (utils/loss.py:17-24) + dL/dpred ---------------------------------------------
         float dpo = 0.f;
         if (valid) {
-            const float zt = 1.0f / (1.0f + expf(-__fdiv_rn(lab, P.sigma)));       // sigmoid(label / sigma)
-            const float e = expf(-fabsf(pown));
-            const float li = fmaxf(pown, 0.f) - pown * zt + log1pf(e);
+            // MUFU-based exp / log / reciprocal (~2 ulp): |d loss| <~ 1e-7, far inside the 2e-5 parity tolerance
+            const float zt = __fdividef(1.0f, 1.0f + __expf(-__fdividef(lab, P.sigma)));   // sigmoid(label / sigma)
+            const float e = __expf(-fabsf(pown));
+            const float li = fmaxf(pown, 0.f) - pown * zt + __logf(1.0f + e);              // log1p(e), e in (0, 1]
             if (half == 0) loss_acc += wgt * li;
             if (TRAIN) {
-                const float sg = pown >= 0.f ? 1.0f / (1.0f + e) : e / (1.0f + e);   // sigmoid(pred)
+                const float rs = __fdividef(1.0f, 1.0f + e);
+                const float sg = pown >= 0.f ? rs : e * rs;                               // sigmoid(pred)
                 dpo = (sg - zt) * wgt * gscale;
             }
         }
@@ -824,14 +845,20 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         // ---- backward: scatter-add into the corner-feature tables (index_put_ accumulate) -------------
         float dx[4];
         from_cfrag(dxc, odd, dx);
+        float qk[kPark];
+        if (kPark == 16) tmem_ld16(tpark, qk); else tmem_ld32(tpark, qk);
+        tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < LMAX; ++i) {
-            if (i < L && slot[i] >= 0) {
+            const int sl = __float_as_int(qk[3 * LMAX + i]);
+            if (i < L && sl >= 0) {
                 const shine_level& lv = P.oct.lv[i];
                 const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
-                const int4 ia = ldg_i4(slots[slot[i]].ids), ib = ldg_i4(slots[slot[i]].ids + 4);
+                const int4 ia = ldg_i4(slots[sl].ids), ib = ldg_i4(slots[sl].ids + 4);
                 const int ids[8] = {ia.x, ib.x, ia.y, ib.y, ia.z, ib.z, ia.w, ib.w};   // un-permute (z-bit-major storage)
-                Blend b; b.init(x, y, z, lv.level, poly);
+                Blend b;
+                b.tx = qk[3 * i]; b.ty = qk[3 * i + 1]; b.tz = qk[3 * i + 2];
+                b.ux = __fsub_rn(1.0f, b.tx); b.uy = __fsub_rn(1.0f, b.ty); b.uz = __fsub_rn(1.0f, b.tz);
                 float* gb = grad_base(lv, (uint32_t)tile, kF) + 4 * half;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -899,11 +926,13 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
             else dst = P.dec.gb3;
             if (dst) atomicAdd(dst, v);
         }
+    }
+    if (TRAIN) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         if (warp == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(smu[SmemPlan::B3 + 1]) : "memory");
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(smu[SmemPlan::B3 + 1]), "n"(kTmemCols > 0 ? kTmemCols : 32) : "memory");
         }
     }
 }
