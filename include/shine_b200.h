@@ -104,6 +104,22 @@ int shine_query_fwd(const shine_octree* oct, const float* coord, int64_t n, floa
  * lv[i].feature_grads[id] += w_c * dfeat[p]  for every hit corner. */
 int shine_query_bwd(const shine_octree* oct, const float* coord, int64_t n, const float* dfeat, void* stream);
 
+/* Coordinate derivatives of query_feature, for the eikonal / normal terms that the reference obtains with
+ * torch.autograd.grad(pred, coord, create_graph=True) (utils/tools.py:175-185, shine_batch.py:141-142,183-185).
+ * With dw_c/da the derivative of the interpolation weight of corner c w.r.t. axis a (incl. the smoothstep and the
+ * 2^level/2 scaling of model/feature_octree.py:173-178):
+ *   coord_grad : out_dcoord[p][a]  = sum_levels sum_c dw_c/da * <features[id_c], dfeat[p]>            ([n,3])
+ *   tangent_fwd: out[p][:]         = sum_levels sum_c (sum_a tangent[p][a] dw_c/da) * features[id_c]   ([n,F])
+ *   tangent_bwd: feature_grads[id_c] += (sum_a tangent[p][a] dw_c/da) * dfeat[p]
+ * coord_grad is the backward of query_fwd w.r.t. coord; tangent_fwd / tangent_bwd are coord_grad's own backward
+ * w.r.t. dfeat / the tables (double backward). */
+int shine_query_coord_grad(const shine_octree* oct, const float* coord, int64_t n, const float* dfeat,
+                           float* out_dcoord, void* stream);
+int shine_query_tangent_fwd(const shine_octree* oct, const float* coord, int64_t n, const float* tangent,
+                            float* out_feat, void* stream);
+int shine_query_tangent_bwd(const shine_octree* oct, const float* coord, int64_t n, const float* tangent,
+                            const float* dfeat, void* stream);
+
 /* query_feature -> Decoder.sdf (model/decoder.py:49-63) fused, forward only (the mesher's query,
  * utils/mesher.py:60-72).  out_pred [n].  out_mask (optional, may be NULL) [n] uint8 = voxel present at
  * lv[mask_level] (utils/mesher.py:82-89). */

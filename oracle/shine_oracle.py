@@ -280,3 +280,24 @@ def cal_feature_importance(octree: OracleOctree, dec: dict, coord_pool, label_po
             importance[k] += g.abs()
             importance[k][-1] *= 0
     return importance
+
+
+def train_step_eikonal(octree: OracleOctree, dec: dict, coord, label, weight, sigma: float, weight_e: float = 0.1):
+    """Loop body with ekional_loss_on (shine_batch.py:119-120,137-142,172-185,208-209): g = d pred / d coord (create_graph)
+    * sigma_sigmoid; eikonal = mean over surface samples of (1 - |g|)^2; loss = bce(mean) + weight_e * eikonal."""
+    for f in octree.hier_features:
+        f.grad = None
+    for p in dec.values():
+        p.grad = None
+    coord = coord.clone().requires_grad_(True)
+    feature = octree.query_feature(coord)
+    pred = decoder_sdf(feature, dec)
+    surface_mask = weight > 0
+    g = torch.autograd.grad(pred, coord, torch.ones_like(pred), create_graph=True, retain_graph=True)[0] * sigma
+    bce = sdf_bce_loss(pred, label, sigma, torch.abs(weight), False, "mean")
+    eik = ((1.0 - g[surface_mask].norm(2, dim=-1)) ** 2).mean()
+    loss = bce + weight_e * eik
+    loss.backward()
+    return {"loss": loss.detach(), "bce": bce.detach(), "eikonal": eik.detach(), "g": g.detach(), "pred": pred.detach(),
+            "table_grads": [f.grad if f.grad is not None else torch.zeros_like(f) for f in octree.hier_features],
+            "dec_grads": {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in dec.items()}}

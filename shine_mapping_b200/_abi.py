@@ -57,6 +57,9 @@ SYMBOLS = {
     "shine_get_indices": (C.c_int, [_OCT, _vp, _i64, _vp, _vp]),
     "shine_query_fwd": (C.c_int, [_OCT, _vp, _i64, _vp, _vp]),
     "shine_query_bwd": (C.c_int, [_OCT, _vp, _i64, _vp, _vp]),
+    "shine_query_coord_grad": (C.c_int, [_OCT, _vp, _i64, _vp, _vp, _vp]),
+    "shine_query_tangent_fwd": (C.c_int, [_OCT, _vp, _i64, _vp, _vp, _vp]),
+    "shine_query_tangent_bwd": (C.c_int, [_OCT, _vp, _i64, _vp, _vp, _vp]),
     "shine_sdf_infer": (C.c_int, [_OCT, _DEC, _vp, _i64, _vp, _vp, _i32, _u32, _vp]),
     "shine_sdf_bce_fwd": (C.c_int, [_OCT, _DEC, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _u32, _vp]),
     "shine_sdf_bce_step": (C.c_int, [_OCT, _DEC, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp, _u32, _vp]),

@@ -10,7 +10,8 @@ checkpoint in the reference's format.  What differs: the body of an iteration is
 
 Out of scope here: dataset I/O (open3d), meshing, visualiser, wandb.  `pool` is anything with the
 `get_batch(bs)` contract of LiDARDataset (dataset/lidar_dataset.py:431-448); `synth.build_scene_map` provides one.
-Configs that need d(pred)/d(coord) (ekional_loss_on etc.) or another loss are rejected explicitly.
+`ekional_loss_on` runs on the class surface (query_feature is differentiable w.r.t. the coordinates, twice); normal /
+consistency / semantic / ray losses are rejected explicitly.
 """
 from __future__ import annotations
 
@@ -27,12 +28,11 @@ from .trainer import SdfTrainer
 
 
 def check_supported(config: SHINEConfig) -> None:
-    unsupported = [k for k in ("ekional_loss_on", "normal_loss_on", "consistency_loss_on", "proj_correction_on",
+    unsupported = [k for k in ("normal_loss_on", "consistency_loss_on", "proj_correction_on",
                                "semantic_on", "time_conditioned", "ray_loss") if getattr(config, k)]
     if unsupported or config.main_loss_type != "sdf_bce":
         raise NotImplementedError(
-            f"the fused sm_100a step implements main_loss_type=sdf_bce without {unsupported or 'extras'}; "
-            "reference configs that switch these on (e.g. kitti_batch.yaml ekional_loss_on) must turn them off")
+            f"implemented: main_loss_type=sdf_bce (+ ekional_loss_on); not {unsupported or config.main_loss_type}")
     if not config.opt_adam:
         raise NotImplementedError("only Adam (reference utils/tools.py:78-79) is implemented")
 
@@ -50,6 +50,27 @@ def save_checkpoint(octree, decoder, trainer, run_path, name, iters):
                 "optimizer": {"exp_avg": trainer.exp_avg, "exp_avg_sq": trainer.exp_avg_sq,
                               "step": trainer.step_count}},
                os.path.join(run_path, f"{name}.pth"))
+
+
+def eikonal_iteration(config: SHINEConfig, octree: FeatureOctree, decoder: Decoder, trainer: SdfTrainer, coord, sdf_label,
+                      weight):
+    """Loop body with ekional_loss_on (reference shine_batch.py:119-120,137-142,172-185,208-209) on the class surface:
+    `query_feature` is differentiable w.r.t. the coordinates (shine_query_coord_grad) and that gradient is itself
+    differentiable (tangent kernels), so the reference's get_gradient(create_graph=True) recipe works as is.  Gradients
+    accumulate into the trainer's flat buffer (param.grad are views of it)."""
+    from .loss import sdf_bce_loss
+    sigma = config.sigma_sigmoid
+    coord = coord.detach().requires_grad_(True)
+    feature = octree.query_feature(coord)
+    pred = decoder.sdf(feature)
+    g = torch.autograd.grad(pred, coord, torch.ones_like(pred), create_graph=True, retain_graph=True)[0] * sigma
+    surface_mask = weight > 0
+    loss = sdf_bce_loss(pred, sdf_label, sigma, torch.abs(weight), config.loss_weight_on, config.loss_reduction)
+    eikonal = ((1.0 - g[surface_mask].norm(2, dim=-1)) ** 2).mean()
+    total = loss + config.weight_e * eikonal
+    total.backward()
+    trainer.loss.copy_(total.detach())
+    return total.detach(), eikonal.detach(), g.detach()
 
 
 class _GraphedIteration:
@@ -96,6 +117,8 @@ def run_shine_mapping_batch(config: SHINEConfig, octree: FeatureOctree, decoder:
     iters = config.iters if iters is None else iters
     if use_cuda_graph is None:
         use_cuda_graph = world == 1
+    if config.ekional_loss_on:
+        use_cuda_graph = False
     graphed = _GraphedIteration(trainer, pool, config.bs) if (use_cuda_graph and world == 1) else None
     trainer.zero_grad()
     losses = {}
@@ -107,6 +130,11 @@ def run_shine_mapping_batch(config: SHINEConfig, octree: FeatureOctree, decoder:
         step_lr_decay(trainer, config.lr, it, config.lr_decay_step, config.lr_iters_reduce_ratio)
         if graphed is not None:
             graphed.run()
+        elif config.ekional_loss_on:
+            coord, sdf_label, weight = pool.get_batch(config.bs)
+            eikonal_iteration(config, octree, decoder, trainer, coord, sdf_label, weight)
+            trainer.all_reduce_grads()
+            trainer.optimizer_step(zero_grad=True)
         else:
             coord, sdf_label, weight = pool.get_batch(config.bs)                       # shine_batch.py:115
             trainer.forward_backward(coord, sdf_label, weight, n_norm=config.bs * world)   # :123-209
@@ -135,7 +163,6 @@ def main(argv=None):
     args = ap.parse_args(argv)
     config = SHINEConfig()
     config.load(args.config)
-    config.ekional_loss_on = False      # see check_supported()
     torch.manual_seed(config.seed)
     octree, decoder = FeatureOctree(config), Decoder(config)
     print("Load, preprocess and sample data (synthetic scans)")

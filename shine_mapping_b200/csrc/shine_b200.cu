@@ -292,6 +292,97 @@ __global__ void __launch_bounds__(256) query_bwd_kernel(const __grid_constant__ 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// coordinate derivatives of query_feature (eikonal / normal terms; reference utils/tools.py:175-185)
+// ------------------------------------------------------------------------------------------------------
+
+// t and dt/dx of one axis: t = smoothstep(frac(res*(0.5x+0.5))) or the linear fraction; dt/dx = t'(d) * res * 0.5
+__device__ __forceinline__ void axis_td(float x, float res, bool poly, float& t, float& dt) {
+    const float c = __fmul_rn(res, __fmaf_rn(x, 0.5f, 0.5f));
+    const float d = c - truncf(c);
+    const float s = res * 0.5f;
+    if (!poly) { t = d; dt = s; return; }
+    const float d2 = __fmul_rn(d, d);
+    t = __fsub_rn(__fmul_rn(3.0f, d2), __fmul_rn(2.0f, __fmul_rn(d2, d)));
+    dt = (6.0f * d - 6.0f * d2) * s;
+}
+
+struct BlendD {   // weights of model/feature_octree.py:186-193 and their derivatives w.r.t. x, y, z
+    float t[3], u[3], dt[3];
+    __device__ __forceinline__ void init(float x, float y, float z, int level, bool poly) {
+        const float res = (float)(1u << level);
+        axis_td(x, res, poly, t[0], dt[0]); axis_td(y, res, poly, t[1], dt[1]); axis_td(z, res, poly, t[2], dt[2]);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) u[a] = 1.0f - t[a];
+    }
+    // dw_c/da for a = 0,1,2
+    __device__ __forceinline__ void dw(int c, float (&g)[3]) const {
+        const float X = (c & 4) ? t[0] : u[0], Y = (c & 2) ? t[1] : u[1], Z = (c & 1) ? t[2] : u[2];
+        const float dX = (c & 4) ? dt[0] : -dt[0], dY = (c & 2) ? dt[1] : -dt[1], dZ = (c & 1) ? dt[2] : -dt[2];
+        g[0] = dX * Y * Z; g[1] = X * dY * Z; g[2] = X * Y * dZ;
+    }
+};
+
+// MODE 0: coord_grad   1: tangent_fwd   2: tangent_bwd
+template <int LP, int MODE>
+__global__ void __launch_bounds__(256) query_tangent_kernel(const __grid_constant__ shine_octree oct,
+                                                            const float* __restrict__ coord, int64_t n,
+                                                            const float* __restrict__ vin,      // dfeat (0,2)
+                                                            const float* __restrict__ tangent,  // [n,3] (1,2)
+                                                            float* __restrict__ out) {
+    constexpr int F = 4 * LP;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t p = gtid / LP;
+    const int part = (int)(gtid % LP);
+    const bool valid = p < n;
+    float x = 0.f, y = 0.f, z = 0.f;
+    float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+    float tg[3] = {0.f, 0.f, 0.f};
+    if (valid) {
+        x = coord[3 * p]; y = coord[3 * p + 1]; z = coord[3 * p + 2];
+        if (MODE != 1) d = ldg_f4(vin + p * F + 4 * part);
+        if (MODE != 0) { tg[0] = tangent[3 * p]; tg[1] = tangent[3 * p + 1]; tg[2] = tangent[3 * p + 2]; }
+    }
+    float g3[3] = {0.f, 0.f, 0.f};
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < oct.num_levels; ++i) {
+        const shine_level& lv = oct.lv[i];
+        const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
+        const int s = valid ? probe_slot(slots, lv.hash_capacity - 1, morton_of(x, y, z, lv.level)) : -1;
+        if (s < 0) continue;
+        const int4 ia = ldg_i4(slots[s].ids), ib = ldg_i4(slots[s].ids + 4);
+        const int ids[8] = {ia.x, ib.x, ia.y, ib.y, ia.z, ib.z, ia.w, ib.w};   // un-permute (z-bit-major storage)
+        BlendD b; b.init(x, y, z, lv.level, oct.poly_interp != 0);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float g[3]; b.dw(c, g);
+            if (MODE == 0) {
+                const float4 v = ldg_f4(lv.features + (int64_t)ids[c] * F + 4 * part);
+                const float q = v.x * d.x + v.y * d.y + v.z * d.z + v.w * d.w;
+                g3[0] = fmaf(g[0], q, g3[0]); g3[1] = fmaf(g[1], q, g3[1]); g3[2] = fmaf(g[2], q, g3[2]);
+            } else {
+                const float w = tg[0] * g[0] + tg[1] * g[1] + tg[2] * g[2];
+                if (MODE == 1) {
+                    const float4 v = ldg_f4(lv.features + (int64_t)ids[c] * F + 4 * part);
+                    acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+                } else {
+                    red_add_f4(lv.feature_grads + (int64_t)ids[c] * F + 4 * part, w * d.x, w * d.y, w * d.z, w * d.w);
+                }
+            }
+        }
+    }
+    if (MODE == 0) {
+#pragma unroll
+        for (int o = 1; o < LP; o <<= 1) {   // the LP lanes of a point are adjacent
+            g3[0] += __shfl_xor_sync(kFull, g3[0], o); g3[1] += __shfl_xor_sync(kFull, g3[1], o); g3[2] += __shfl_xor_sync(kFull, g3[2], o);
+        }
+        if (valid && part == 0) { out[3 * p] = g3[0]; out[3 * p + 1] = g3[1]; out[3 * p + 2] = g3[2]; }
+    } else if (MODE == 1) {
+        if (valid) *reinterpret_cast<float4*>(out + p * F + 4 * part) = acc;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // tensor-core helpers: mma.sync m16n8k8 TF32, fp32 accumulate, optional 3xTF32 error compensation
 // ------------------------------------------------------------------------------------------------------
@@ -1411,6 +1502,22 @@ int dispatch_query(bool bwd, const shine_octree* oct, const float* coord, int64_
     }
 }
 
+template <int MODE>
+int dispatch_tangent(const shine_octree* oct, const float* coord, int64_t n, const float* vin, const float* tangent,
+                     float* out, cudaStream_t st) {
+    const int lp = oct->feature_dim / 4;
+    const int64_t blocks = (n * lp + 255) / 256;
+    if (blocks > INT32_MAX) return SHINE_ERR_UNSUPPORTED;
+    switch (lp) {
+        case 1: query_tangent_kernel<1, MODE><<<(unsigned)blocks, 256, 0, st>>>(*oct, coord, n, vin, tangent, out); break;
+        case 2: query_tangent_kernel<2, MODE><<<(unsigned)blocks, 256, 0, st>>>(*oct, coord, n, vin, tangent, out); break;
+        case 4: query_tangent_kernel<4, MODE><<<(unsigned)blocks, 256, 0, st>>>(*oct, coord, n, vin, tangent, out); break;
+        case 8: query_tangent_kernel<8, MODE><<<(unsigned)blocks, 256, 0, st>>>(*oct, coord, n, vin, tangent, out); break;
+        default: return SHINE_ERR_UNSUPPORTED;
+    }
+    return (int)cudaGetLastError();
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------
@@ -1470,6 +1577,33 @@ int shine_query_bwd(const shine_octree* oct, const float* coord, int64_t n, cons
     if (n < 0 || (n > 0 && (!coord || !dfeat))) return SHINE_ERR_INVALID_ARG;
     if (n == 0) return SHINE_OK;
     return dispatch_query(true, oct, coord, n, nullptr, dfeat, (cudaStream_t)stream);
+}
+
+int shine_query_coord_grad(const shine_octree* oct, const float* coord, int64_t n, const float* dfeat, float* out_dcoord,
+                           void* stream) {
+    int rc = check_octree(oct, false);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!coord || !dfeat || !out_dcoord))) return SHINE_ERR_INVALID_ARG;
+    if (n == 0) return SHINE_OK;
+    return dispatch_tangent<0>(oct, coord, n, dfeat, nullptr, out_dcoord, (cudaStream_t)stream);
+}
+
+int shine_query_tangent_fwd(const shine_octree* oct, const float* coord, int64_t n, const float* tangent, float* out_feat,
+                            void* stream) {
+    int rc = check_octree(oct, false);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!coord || !tangent || !out_feat))) return SHINE_ERR_INVALID_ARG;
+    if (n == 0) return SHINE_OK;
+    return dispatch_tangent<1>(oct, coord, n, nullptr, tangent, out_feat, (cudaStream_t)stream);
+}
+
+int shine_query_tangent_bwd(const shine_octree* oct, const float* coord, int64_t n, const float* tangent,
+                            const float* dfeat, void* stream) {
+    int rc = check_octree(oct, true);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!coord || !tangent || !dfeat))) return SHINE_ERR_INVALID_ARG;
+    if (n == 0) return SHINE_OK;
+    return dispatch_tangent<2>(oct, coord, n, dfeat, tangent, nullptr, (cudaStream_t)stream);
 }
 
 int shine_sdf_infer(const shine_octree* oct, const shine_decoder* dec, const float* coord, int64_t n, float* out_pred,

@@ -101,9 +101,51 @@ class _LevelState:
 # --------------------------------------------------------------------------------------------------------
 
 
+class _QueryCoordGrad(torch.autograd.Function):
+    """G[p,a] = sum_levels sum_c dw_c/da <f_c, dfeat_p>: the backward of query_feature w.r.t. the coordinates, itself
+    differentiable w.r.t. dfeat and the tables (what `autograd.grad(pred, coord, create_graph=True)` needs for the
+    eikonal / normal losses, reference utils/tools.py:175-185)."""
+
+    @staticmethod
+    def forward(ctx, octree, coord, dfeat, *tables):
+        n = coord.shape[0]
+        dfeat = dfeat.contiguous()
+        out = torch.empty(n, 3, dtype=torch.float32, device=coord.device)
+        desc = octree._descriptor(tables, None)
+        _abi.check(_abi.lib().shine_query_coord_grad(C.byref(desc), _abi.ptr(coord), n, _abi.ptr(dfeat), _abi.ptr(out),
+                                                     _abi.stream_ptr(coord.device)), "shine_query_coord_grad")
+        ctx.octree = octree
+        ctx.save_for_backward(coord, dfeat, *tables)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dG):
+        coord, dfeat, *tables = ctx.saved_tensors
+        octree = ctx.octree
+        n = coord.shape[0]
+        dG = dG.contiguous()
+        lib, stream = _abi.lib(), _abi.stream_ptr(coord.device)
+        d_dfeat = None
+        if ctx.needs_input_grad[2]:
+            d_dfeat = torch.empty_like(dfeat)
+            desc = octree._descriptor(tables, None)
+            _abi.check(lib.shine_query_tangent_fwd(C.byref(desc), _abi.ptr(coord), n, _abi.ptr(dG), _abi.ptr(d_dfeat),
+                                                   stream), "shine_query_tangent_fwd")
+        grads = [None] * len(tables)
+        if any(ctx.needs_input_grad[3:]):
+            full = [torch.zeros_like(t) for t in tables]
+            desc = octree._descriptor(tables, full)
+            _abi.check(lib.shine_query_tangent_bwd(C.byref(desc), _abi.ptr(coord), n, _abi.ptr(dG), _abi.ptr(dfeat),
+                                                   stream), "shine_query_tangent_bwd")
+            grads = [g if need else None for g, need in zip(full, ctx.needs_input_grad[3:])]
+        return (None, None, d_dfeat, *grads)
+
+
 class _QueryFeature(torch.autograd.Function):
     """query_feature forward = shine_query_fwd, backward = shine_query_bwd (dense grads like the reference's
-    index_put_(accumulate=True), but scatter-added with vector atomics and misses skipped)."""
+    index_put_(accumulate=True), but scatter-added with vector atomics and misses skipped); the gradient w.r.t. the
+    coordinates is `_QueryCoordGrad`, which supports a second backward."""
 
     @staticmethod
     def forward(ctx, octree, coord, *tables):
@@ -120,16 +162,20 @@ class _QueryFeature(torch.autograd.Function):
     def backward(ctx, dfeat):
         coord, *tables = ctx.saved_tensors
         octree = ctx.octree
-        grads = [torch.zeros_like(t) if need else None
-                 for t, need in zip(tables, ctx.needs_input_grad[2:])]
-        if any(g is not None for g in grads):
-            full = [g if g is not None else torch.zeros_like(t) for g, t in zip(grads, tables)]
-            desc = octree._descriptor(tables, full, n_points=coord.shape[0])
-            dfeat = dfeat.contiguous()
-            _abi.check(_abi.lib().shine_query_bwd(C.byref(desc), _abi.ptr(coord), coord.shape[0], _abi.ptr(dfeat),
-                                                  _abi.stream_ptr(coord.device)), "shine_query_bwd")
-            octree._reduce_replicas(desc, coord.device)
-        return (None, None, *grads)
+        grads = [None] * len(tables)
+        if any(ctx.needs_input_grad[2:]):
+            with torch.no_grad():
+                full = [torch.zeros_like(t) for t in tables]
+                desc = octree._descriptor(tables, full, n_points=coord.shape[0])
+                d = dfeat.detach().contiguous()
+                _abi.check(_abi.lib().shine_query_bwd(C.byref(desc), _abi.ptr(coord), coord.shape[0], _abi.ptr(d),
+                                                      _abi.stream_ptr(coord.device)), "shine_query_bwd")
+                octree._reduce_replicas(desc, coord.device)
+            grads = [g if need else None for g, need in zip(full, ctx.needs_input_grad[2:])]
+        dcoord = None
+        if ctx.needs_input_grad[1]:
+            dcoord = _QueryCoordGrad.apply(octree, coord.detach(), dfeat, *tables)
+        return (None, dcoord, *grads)
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -454,10 +500,6 @@ class FeatureOctree(nn.Module):
     def query_feature(self, coord, faster=False):
         """All-in-one feature query (reference :237-244): one kernel that hashes the point into each level,
         gathers the 8 corner rows, blends and sums over levels; autograd scatter-adds into the tables."""
-        if coord.requires_grad:
-            raise NotImplementedError(
-                "d(feature)/d(coord) (eikonal / normal losses, reference utils/tools.py:175-185) is not part of the "
-                "sm_100a hot path yet; run with ekional_loss_on=False")
         self.set_zero()
         coord = self._prep_coord(coord)
         self._last_coord = coord

@@ -118,6 +118,37 @@ def test_tcgen05_infer_matches_oracle(levels, n_batch):
     assert (pred - ref).abs().max() < 1e-5
 
 
+@pytest.mark.parametrize("levels,poly", [(2, True), (4, True), (3, False)])
+def test_eikonal_through_class_surface_matches_oracle(levels, poly):
+    """ekional_loss_on (reference shine_batch.py:141-142,183-185): d pred / d coord with create_graph=True through
+    query_feature's coordinate-gradient kernels, and the second backward through the tangent kernels."""
+    from oracle import shine_oracle as orc
+    from shine_mapping_b200 import SdfTrainer
+    from shine_mapping_b200.batch_loop import eikonal_iteration
+    from tests.parity_utils import oracle_from_case
+    case = make_case(n_points=2000, n_batch=1500, feat_levels=levels, seed=100 + levels, poly=poly)
+    cfg, octree, dec = build_cuda_models(case, DEV)
+    cfg.ekional_loss_on, cfg.weight_e = True, 0.1
+    coord = torch.from_numpy(case["coord"]).to(DEV); label = torch.from_numpy(case["label"]).to(DEV)
+    weight = torch.from_numpy(case["weight"]).to(DEV)
+    tr = SdfTrainer(cfg, octree, dec)
+    tr.zero_grad()
+    total, eik, g = eikonal_iteration(cfg, octree, dec, tr, coord, label, weight)
+    o, odec = oracle_from_case(case)
+    want = orc.train_step_eikonal(o, odec, torch.from_numpy(case["coord"]), torch.from_numpy(case["label"]),
+                                  torch.from_numpy(case["weight"]), case["cfg"]["sigma"], 0.1)
+    gw = want["g"].numpy()
+    assert np.abs(g.cpu().numpy() - gw).max() <= 1e-4 * np.abs(gw).max() + 1e-7
+    assert abs(float(eik) - float(want["eikonal"])) <= 1e-4 * abs(float(want["eikonal"])) + 1e-7
+    assert abs(float(total) - float(want["loss"])) <= 1e-4 * abs(float(want["loss"]))
+    for k, gt in enumerate(want["table_grads"]):
+        got = tr.table_grads[k].cpu().numpy()
+        assert np.abs(got - gt.numpy())[:-1].max() <= 1e-3 * np.abs(gt.numpy()).max() + 1e-9, k
+    for name, p in zip(DEC_KEYS, dec.fused_params()):
+        gt = want["dec_grads"][name].numpy()
+        assert np.abs(p.grad.cpu().numpy() - gt).max() <= 1e-3 * np.abs(gt).max() + 1e-9, name
+
+
 def test_points_to_morton_bit_exact():
     from shine_mapping_b200 import _abi
     from oracle import shine_oracle as orc
