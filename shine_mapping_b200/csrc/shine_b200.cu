@@ -562,8 +562,9 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
     // Tensor-Memory parking areas of this warp (lanes 32*(warp&3).., column group warp>>2):
     //   tpark: per-tile state that must survive the MLP phase (blend factors tx,ty,tz of every level + slot indices)
     //   tacc : decoder-gradient accumulators (DEC_GRAD only)
-    constexpr int kPark = LMAX <= 4 ? 16 : 32;                           // floats parked per lane
-    constexpr int kColsPerGroup = DEC_GRAD ? 128 : kPark;                // 56 acc (+pad to 64) + park
+    constexpr int kPark = LMAX <= 4 ? 16 : 32;                           // blend factors + slots parked per lane
+    constexpr int kIdPark = 4 * LMAX;                                    // this lane's 4 corner rows of every level
+    constexpr int kColsPerGroup = DEC_GRAD ? 128 : (kPark + kIdPark);    // 56 acc (+pad to 64) + park + ids
     constexpr int kTmemCols = TRAIN ? 2 * kColsPerGroup : 0;             // 256 (dec grads) / 32 / 64, power of two
     uint32_t tacc = 0, tpark = 0;
     if (TRAIN) {
@@ -698,10 +699,13 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         //      channels of its row-half. ----
         float feat[4];
         float pk[kPark];   // [3i..3i+2] = tx,ty,tz of level i; [3*LMAX + i] = slot index (parked in TMEM over the MLP)
+        float idp[kIdPark];   // [4i..4i+3] = rows of this lane's corners (z bit == half) of level i
         {
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int i = 0; i < kPark; ++i) pk[i] = 0.f;
+#pragma unroll
+            for (int i = 0; i < kIdPark; ++i) idp[i] = 0.f;
 #pragma unroll
             for (int i = 0; i < LMAX; ++i) {
                 if (i < L && slot[i] >= 0) {
@@ -711,6 +715,8 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                     // two lanes of a pair then fetch z-neighbours, whose rows are consecutive in the table (lexicographic
                     // numbering) and usually share a 128-byte line -> one L1TEX wavefront instead of two
                     const int4 id4 = ldg_i4(slots[slot[i]].ids + 4 * half);
+                    idp[4 * i] = __int_as_float(id4.x); idp[4 * i + 1] = __int_as_float(id4.y);
+                    idp[4 * i + 2] = __int_as_float(id4.z); idp[4 * i + 3] = __int_as_float(id4.w);
                     float r0[8], r1[8], r2[8], r3[8];
                     ldg_row8(lv.features + (int64_t)id4.x * kF, r0);
                     ldg_row8(lv.features + (int64_t)id4.y * kF, r1);
@@ -740,6 +746,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
 #pragma unroll
             for (int i = 0; i < LMAX; ++i) pk[3 * LMAX + i] = __int_as_float(slot[i]);
             if (kPark == 16) tmem_st16(tpark, pk); else tmem_st32(tpark, pk);
+            if (kIdPark == 16) tmem_st16(tpark + kPark, idp); else tmem_st32(tpark + kPark, idp);
             tmem_wait_st();
         }
         if (!TRAIN && P.mask) {
@@ -936,17 +943,24 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         // ---- backward: scatter-add into the corner-feature tables (index_put_ accumulate) -------------
         float dx[4];
         from_cfrag(dxc, odd, dx);
-        float qk[kPark];
+        float qk[kPark], qid[kIdPark];
         if (kPark == 16) tmem_ld16(tpark, qk); else tmem_ld32(tpark, qk);
+        if (kIdPark == 16) tmem_ld16(tpark + kPark, qid); else tmem_ld32(tpark + kPark, qid);
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < LMAX; ++i) {
             const int sl = __float_as_int(qk[3 * LMAX + i]);
+            // the 8 corner rows: this lane kept the 4 with z bit == half, its partner (lane ^ 2) the other 4
+            int ids[8];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int mine = __float_as_int(qid[4 * i + k]);
+                const int other = __shfl_xor_sync(kFull, mine, 2);
+                ids[2 * k] = half ? other : mine;
+                ids[2 * k + 1] = half ? mine : other;
+            }
             if (i < L && sl >= 0) {
                 const shine_level& lv = P.oct.lv[i];
-                const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
-                const int4 ia = ldg_i4(slots[sl].ids), ib = ldg_i4(slots[sl].ids + 4);
-                const int ids[8] = {ia.x, ib.x, ia.y, ib.y, ia.z, ib.z, ia.w, ib.w};   // un-permute (z-bit-major storage)
                 Blend b;
                 b.tx = qk[3 * i]; b.ty = qk[3 * i + 1]; b.tz = qk[3 * i + 2];
                 b.ux = __fsub_rn(1.0f, b.tx); b.uy = __fsub_rn(1.0f, b.ty); b.uz = __fsub_rn(1.0f, b.tz);

@@ -35,9 +35,17 @@ def test_batch_loop_trains_and_checkpoints(tmp_path, built_lib):
     restored = ck["feature_octree"]
     coord, _, _ = pool.get_batch(1000)
     assert torch.equal(restored.query_feature(coord), octree.query_feature(coord))    # hash rebuilt after unpickle
-    cfg.ekional_loss_on = True
+    cfg.normal_loss_on = True
     with pytest.raises(NotImplementedError):
         check_supported(cfg)
+    cfg.normal_loss_on = False
+    # the shipped KITTI batch config has ekional_loss_on: True (config/kitti/kitti_batch.yaml:46)
+    cfg.ekional_loss_on, cfg.weight_e, cfg.iters, cfg.bs = True, 0.1, 60, 2048
+    torch.manual_seed(42)
+    octree3, decoder3 = FeatureOctree(cfg), Decoder(cfg)
+    pool3 = synth.build_scene_map(cfg, octree3, n_azimuth=256, n_frames=1, seed=42, device=DEV)
+    out3 = run_shine_mapping_batch(cfg, octree3, decoder3, pool3)
+    assert np.isfinite(out3["loss_last"]) and out3["loss_last"] < out3["loss_first"], out3
 
 
 def _free_port():
