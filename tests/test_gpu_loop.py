@@ -110,7 +110,7 @@ def test_step_from_host_matches_resident_step(built_lib):
     g_host = tr.flat_grad.clone()
     tr.zero_grad()
     loss_res = float(tr.forward_backward(coord_h.to(DEV), label_h.to(DEV)))
-    assert abs(loss_host - loss_res) <= 2e-6 * abs(loss_res)
+    assert abs(loss_host - loss_res) <= 2e-5 * abs(loss_res)      # fp32 atomic accumulation order differs
     assert (g_host - tr.flat_grad).abs().max() <= 1e-4 * tr.flat_grad.abs().max()
 
 
