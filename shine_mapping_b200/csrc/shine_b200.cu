@@ -1299,9 +1299,21 @@ __global__ void __launch_bounds__(256) reduce_replicas_kernel(const __grid_const
     float4* main4 = reinterpret_cast<float4*>(lv.feature_grads);
     float4* rep4 = reinterpret_cast<float4*>(lv.grad_replicas);
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nrep = lv.num_replicas - 1;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 acc = main4[i];
-        for (int r = 0; r < lv.num_replicas - 1; ++r) {
+        int r = 0;
+        for (; r + 8 <= nrep; r += 8) {          // 8 independent loads in flight per thread
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = rep4[(int64_t)(r + u) * n4 + i];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+                rep4[(int64_t)(r + u) * n4 + i] = zero;
+            }
+        }
+        for (; r < nrep; ++r) {
             const float4 v = rep4[(int64_t)r * n4 + i];
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
             rep4[(int64_t)r * n4 + i] = zero;
@@ -1689,7 +1701,7 @@ int shine_reduce_grad_replicas(const shine_octree* oct, void* stream) {
         }
     if (max_n4 == 0) return SHINE_OK;
     int64_t blocks = (max_n4 + 255) / 256;
-    const int64_t cap = (int64_t)sm_count() * 4;
+    const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
     dim3 grid((unsigned)blocks, (unsigned)oct->num_levels);
     reduce_replicas_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*oct);

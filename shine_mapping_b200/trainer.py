@@ -67,7 +67,9 @@ class SdfTrainer:
         for s in sizes:
             offs.append(total)
             total += _align4(s)
-        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        # + 4 floats at the end: the loss accumulator lives in the same allocation, so zero_grad() clears it for free
+        self._flat_all = torch.zeros(total + 4, dtype=torch.float32, device=dev)
+        self.flat_grad = self._flat_all[:total]
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         self.step_count = 0   # fresh Adam state, like a rebuilt torch optimizer
@@ -84,10 +86,12 @@ class SdfTrainer:
             if p is not None and p.requires_grad:
                 p.grad = g
         self._sig = sig
-        self.loss = torch.zeros((), dtype=torch.float32, device=dev)
+        self.loss = self._flat_all[total:total + 1].view(())
+        self._loss_clean = True
 
     def zero_grad(self):
-        self.flat_grad.zero_()
+        self._flat_all.zero_()       # gradients AND the loss accumulator: one memset
+        self._loss_clean = True
 
     # ---- the hot path --------------------------------------------------------------------------------------
 
@@ -103,8 +107,9 @@ class SdfTrainer:
         scale = 1.0 if cfg.loss_reduction == "sum" else 1.0 / float(n_norm if n_norm else n)
         od = self.octree._descriptor(None, self.table_grads, n_points=n if self.use_replicas else 0)
         dd = self.decoder.c_descriptor(self.dec_grads if self._dec_trainable else None)
-        if not accumulate_loss:
+        if not accumulate_loss and not self._loss_clean:
             self.loss.zero_()
+        self._loss_clean = False
         _abi.check(_abi.lib().shine_sdf_bce_step(
             C.byref(od), C.byref(dd), _abi.ptr(coord), _abi.ptr(sdf_label),
             _abi.ptr(weight) if weighted else None, n, float(self.sigma), scale, None,
@@ -167,7 +172,7 @@ class SdfTrainer:
 
     # ---- host-buffer entry (the reference-facing call with HOST memory) -----------------------------------------
 
-    def step_from_host(self, coord_h, label_h, weight_h=None, optimizer: bool = False, chunks: int = 4) -> float:
+    def step_from_host(self, coord_h, label_h, weight_h=None, optimizer: bool = False, chunks: int = 2) -> float:
         """coord/label(/weight) are (pinned) host tensors.  The batch is cut into `chunks` slices: slice k+1 is copied
         host->device on a copy stream while the fused kernel runs on slice k (gradients and the loss accumulate
         across slices; the per-point scale uses the whole batch), then the loss is read back."""
