@@ -21,16 +21,7 @@
 
 #include "shine_b200.h"
 
-// tuning switches (defaults = the best measured on B200; see profiles/)
-#ifndef SHINE_SPEC_IDS
-#define SHINE_SPEC_IDS 0      // fetch the 8 corner ids speculatively together with the first-probe key
-#endif
-#ifndef SHINE_PARALLEL_PROBE
-#define SHINE_PARALLEL_PROBE 0 // issue every level's first-probe key load before resolving any (costs registers)
-#endif
-#ifndef SHINE_HASH32
-#define SHINE_HASH32 0        // 32-bit fmix32 hash of the folded key (else the 64-bit two-multiply mix)
-#endif
+// tuning switches (defaults = the best measured on B200; every alternative is in profiles/r01_summary.md)
 #ifndef SHINE_PREFETCH
 #define SHINE_PREFETCH 1      // software-pipeline the next tile's coord/label loads
 #endif
@@ -62,20 +53,13 @@ struct __align__(64) HashSlot {
 };
 static_assert(sizeof(HashSlot) == SHINE_HASH_SLOT_BYTES, "slot must be 64 bytes");
 
+// 64-bit mix (two multiplies).  A cheaper 32-bit fmix32 of the folded key was measured and rejected: more first-probe
+// collisions (gather-only kernel 0.111 -> 0.137 ms).
 __host__ __device__ __forceinline__ uint32_t hash_key(unsigned long long k) {
-#if SHINE_HASH32
-    // 32-bit finaliser (murmur3 fmix32) over the folded key: ~9 integer ops instead of two 64-bit multiplies
-    uint32_t x = (uint32_t)k ^ ((uint32_t)(k >> 32) * 0x9E3779B1u);
-    x ^= x >> 16; x *= 0x85EBCA6Bu;
-    x ^= x >> 13; x *= 0xC2B2AE35u;
-    x ^= x >> 16;
-    return x;
-#else
     k ^= k >> 31; k *= 0x9E3779B97F4A7C15ull;
     k ^= k >> 29; k *= 0xBF58476D1CE4E5B9ull;
     k ^= k >> 32;
     return (uint32_t)k;
-#endif
 }
 
 // bit i of v -> bit 3i (16 significant bits, as kaolin's int16 coordinates)
@@ -1144,79 +1128,101 @@ __global__ void __launch_bounds__(128, 5) sdf_infer_tc_kernel(const __grid_const
     const int rg = tid >> 3, r0 = tid & 7;                                   // 8-row group / row within it
     const int num_tiles = (int)((P.n + 127) / 128);
 
+    const int half = tid & 1;                                              // gather: two adjacent lanes per point
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int64_t p = (int64_t)tile * 128 + tid;
-        const bool valid = p < P.n;
-        float x = 0.f, y = 0.f, z = 0.f;
-        if (valid) { x = __ldg(P.coord + 3 * p); y = __ldg(P.coord + 3 * p + 1); z = __ldg(P.coord + 3 * p + 2); }
-
-        // ---- hash walk + gather + blend: one thread does the whole point --------------------------------------
-        float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        bool present = false;
-        {
-            const unsigned long long key0 = valid ? morton_of(x, y, z, P.oct.lv[0].level) : 0ull;
+        // ---- hash walk + gather + blend with two lanes per point (levels split for probing, corners split by z bit so
+        //      the pair's two LDG.256 of one instruction hit z-neighbour rows = usually one 128-byte line); two passes of
+        //      64 points fill the 128-row A tile ----
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            const int row = pass * 64 + (tid >> 1);
+            const int64_t p = (int64_t)tile * 128 + row;
+            const bool valid = p < P.n;
+            float x = 0.f, y = 0.f, z = 0.f;
+            if (valid) { x = __ldg(P.coord + 3 * p); y = __ldg(P.coord + 3 * p + 1); z = __ldg(P.coord + 3 * p + 2); }
             int slot[LMAX];
-            unsigned long long kq[LMAX], kf[LMAX];
+            {
+                constexpr int LH = LMAX / 2;
+                const unsigned long long key0 = valid ? morton_of(x, y, z, P.oct.lv[0].level) : 0ull;
+                unsigned long long kq[LH], kf[LH];
+                int mine[LH];
 #pragma unroll
-            for (int i = 0; i < LMAX; ++i) {          // first-probe keys of every level in flight together
-                slot[i] = -1;
-                if (i < L && valid) {
-                    const shine_level& lv = P.oct.lv[i];
-                    kq[i] = consecutive ? (key0 >> (3 * i)) : morton_of(x, y, z, lv.level);
-                    slot[i] = (int)(hash_key(kq[i]) & (lv.hash_capacity - 1));
-                    kf[i] = __ldg(&reinterpret_cast<const HashSlot*>(lv.hash_slots)[slot[i]].key);
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < LMAX; ++i) {
-                if (i < L && valid && kf[i] != kq[i]) {
-                    if (kf[i] == kEmptyKey) slot[i] = -1;
-                    else {
+                for (int j = 0; j < LH; ++j) {
+                    const int i = 2 * j + half;
+                    mine[j] = -1;
+                    if (i < L && valid) {
                         const shine_level& lv = P.oct.lv[i];
-                        slot[i] = probe_slot_from(reinterpret_cast<const HashSlot*>(lv.hash_slots), lv.hash_capacity - 1,
-                                                  kq[i], (uint32_t)slot[i] + 1);
+                        kq[j] = consecutive ? (key0 >> (3 * i)) : morton_of(x, y, z, lv.level);
+                        mine[j] = (int)(hash_key(kq[j]) & (lv.hash_capacity - 1));
+                        kf[j] = __ldg(&reinterpret_cast<const HashSlot*>(lv.hash_slots)[mine[j]].key);
                     }
                 }
-                if (i == P.mask_level) present = slot[i] >= 0;
+#pragma unroll
+                for (int j = 0; j < LH; ++j) {
+                    const int i = 2 * j + half;
+                    if (i < L && valid && kf[j] != kq[j]) {
+                        if (kf[j] == kEmptyKey) mine[j] = -1;
+                        else {
+                            const shine_level& lv = P.oct.lv[i];
+                            mine[j] = probe_slot_from(reinterpret_cast<const HashSlot*>(lv.hash_slots), lv.hash_capacity - 1,
+                                                      kq[j], (uint32_t)mine[j] + 1);
+                        }
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < LH; ++j) {
+                    const int other = __shfl_xor_sync(kFull, mine[j], 1);
+                    slot[2 * j] = half ? other : mine[j];
+                    slot[2 * j + 1] = half ? mine[j] : other;
+                }
             }
+            if (P.mask && valid && half == 0) {
+                bool present = false;
+#pragma unroll
+                for (int i = 0; i < LMAX; ++i) present = (i == P.mask_level) ? (slot[i] >= 0) : present;
+                P.mask[p] = (uint8_t)present;
+            }
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int i = 0; i < LMAX; ++i) {
                 if (i < L && slot[i] >= 0) {
                     const shine_level& lv = P.oct.lv[i];
                     const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
+                    const int4 id4 = ldg_i4(slots[slot[i]].ids + 4 * half);       // corners with z bit == half
+                    float q0[8], q1[8], q2[8], q3[8];
+                    ldg_row8(lv.features + (int64_t)id4.x * kF, q0);
+                    ldg_row8(lv.features + (int64_t)id4.y * kF, q1);
+                    ldg_row8(lv.features + (int64_t)id4.z * kF, q2);
+                    ldg_row8(lv.features + (int64_t)id4.w * kF, q3);
                     Blend b; b.init(x, y, z, lv.level, poly);
+                    const float wz = half ? b.tz : b.uz;
+                    const float w0 = __fmul_rn(__fmul_rn(b.ux, b.uy), wz), w1 = __fmul_rn(__fmul_rn(b.ux, b.ty), wz);
+                    const float w2 = __fmul_rn(__fmul_rn(b.tx, b.uy), wz), w3 = __fmul_rn(__fmul_rn(b.tx, b.ty), wz);
 #pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {                       // corners hh, 2+hh, 4+hh, 6+hh
-                        const int4 id4 = ldg_i4(slots[slot[i]].ids + 4 * hh);
-                        float q0[8], q1[8], q2[8], q3[8];
-                        ldg_row8(lv.features + (int64_t)id4.x * kF, q0);
-                        ldg_row8(lv.features + (int64_t)id4.y * kF, q1);
-                        ldg_row8(lv.features + (int64_t)id4.z * kF, q2);
-                        ldg_row8(lv.features + (int64_t)id4.w * kF, q3);
-                        const float w0 = b.w(hh), w1 = b.w(2 + hh), w2 = b.w(4 + hh), w3 = b.w(6 + hh);   // z-bit-major ids
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            float a = f[q];
-                            a = fmaf(w0, q0[q], a); a = fmaf(w1, q1[q], a); a = fmaf(w2, q2[q], a); a = fmaf(w3, q3[q], a);
-                            f[q] = a;
-                        }
+                    for (int q = 0; q < 8; ++q) {
+                        float a = acc[q];
+                        a = fmaf(w0, q0[q], a); a = fmaf(w1, q1[q], a); a = fmaf(w2, q2[q], a); a = fmaf(w3, q3[q], a);
+                        acc[q] = a;
                     }
                 }
             }
+            // each lane keeps the 4 channels of its half (= one 16-byte K-chunk of the point's row of the A tile)
+            uint32_t h4[4], l4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float send = half ? acc[q] : acc[4 + q];
+                const float recv = __shfl_xor_sync(kFull, send, 1);
+                split_fast((half ? acc[4 + q] : acc[q]) + recv, h4[q], l4[q]);
+            }
+            const int off = (row >> 3) * 256 + half * 128 + (row & 7) * 16;
+            *reinterpret_cast<uint4*>(tsm + TcPlan::A1H + off) = make_uint4(h4[0], h4[1], h4[2], h4[3]);
+            *reinterpret_cast<uint4*>(tsm + TcPlan::A1L + off) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
         }
-        if (P.mask && valid) P.mask[p] = (uint8_t)present;
+        const int64_t p = (int64_t)tile * 128 + tid;          // epilogues: one thread per row of the tile
+        const bool valid = p < P.n;
 
         // ---- layer 1 on the tensor core ----------------------------------------------------------------------------
-        {
-            uint32_t h[8], l[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) split_fast(f[q], h[q], l[q]);
-            const int off = rg * 256 + r0 * 16;
-            *reinterpret_cast<uint4*>(tsm + TcPlan::A1H + off) = make_uint4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<uint4*>(tsm + TcPlan::A1H + off + 128) = make_uint4(h[4], h[5], h[6], h[7]);
-            *reinterpret_cast<uint4*>(tsm + TcPlan::A1L + off) = make_uint4(l[0], l[1], l[2], l[3]);
-            *reinterpret_cast<uint4*>(tsm + TcPlan::A1L + off + 128) = make_uint4(l[4], l[5], l[6], l[7]);
-        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
