@@ -151,7 +151,7 @@ def run_cuda_step(case, device="cuda:0", single_pass=True, tf32x1=False, unfused
     torch.cuda.synchronize()
     return {
         "indices": indices, "feature": feature.detach().cpu().numpy(), "pred": pred.detach().cpu().numpy(),
-        "loss": float(loss),
+        "loss": float(loss.detach()),
         "table_grads": [p.grad.cpu().numpy() for p in octree.hier_features],
         "dec_grads": {k: dict(dec.named_parameters())[k].grad.cpu().numpy() for k in DEC_KEYS},
     }

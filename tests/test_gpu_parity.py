@@ -35,6 +35,7 @@ def test_cuda_matches_reference_golden(name):
 @pytest.mark.parametrize("levels,poly,weighted,reduction,frames", [
     (1, True, False, "mean", 1), (2, True, False, "mean", 1), (3, False, True, "sum", 2),
     (4, True, False, "mean", 1), (4, True, True, "mean", 2), (4, False, False, "sum", 1),
+    (6, True, False, "mean", 1), (8, True, True, "sum", 2),        # > 4 levels: the LMAX = 8 kernel instantiations
 ])
 def test_fused_step_matches_oracle(levels, poly, weighted, reduction, frames):
     case = make_case(n_points=2500, n_batch=3000, feat_levels=levels, seed=10 + levels, n_frames=frames,
@@ -100,9 +101,15 @@ def test_infer_and_mask_match_step_pred():
         pred, mask = sdf_infer(octree, dec, coord, mask_level=lvl)
         assert np.abs(pred.cpu().numpy() - want["pred"]).max() < 2e-5
         assert np.array_equal(mask.cpu().numpy(), (want["indices"][lvl] >= 0).all(1))
+    case6 = make_case(n_points=2500, n_batch=3000, feat_levels=7, seed=37)       # LMAX = 8 instantiation
+    cfg6, octree6, dec6 = build_cuda_models(case6, DEV)
+    want6 = run_oracle_step(case6)
+    pred6, mask6 = sdf_infer(octree6, dec6, torch.from_numpy(case6["coord"]).to(DEV), mask_level=5)
+    assert np.abs(pred6.cpu().numpy() - want6["pred"]).max() < 2e-5
+    assert np.array_equal(mask6.cpu().numpy(), (want6["indices"][5] >= 0).all(1))
 
 
-@pytest.mark.parametrize("levels,n_batch", [(4, 3000), (2, 100), (3, 40000)])
+@pytest.mark.parametrize("levels,n_batch", [(4, 3000), (2, 100), (3, 40000), (6, 3000)])
 def test_tcgen05_infer_matches_oracle(levels, n_batch):
     """tcgen05.mma / TMEM decoder (SHINE_FLAG_TCGEN05) vs the oracle and vs the mma.sync kernel, incl. the mask."""
     from shine_mapping_b200 import sdf_infer
@@ -118,7 +125,7 @@ def test_tcgen05_infer_matches_oracle(levels, n_batch):
     assert (pred - ref).abs().max() < 1e-5
 
 
-@pytest.mark.parametrize("levels,poly", [(2, True), (4, True), (3, False)])
+@pytest.mark.parametrize("levels,poly", [(2, True), (4, True), (3, False), (6, True)])
 def test_eikonal_through_class_surface_matches_oracle(levels, poly):
     """ekional_loss_on (reference shine_batch.py:141-142,183-185): d pred / d coord with create_graph=True through
     query_feature's coordinate-gradient kernels, and the second backward through the tangent kernels."""
