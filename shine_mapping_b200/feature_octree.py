@@ -398,7 +398,7 @@ class FeatureOctree(nn.Module):
 
     # Same-address red.add serialises in L2: a level with few rows that receives many updates per step is
     # privatised into R replicas (R = pow2, chosen so that a row sees about _REPLICA_TARGET updates per replica).
-    _REPLICA_TARGET = int(os.environ.get("SHINE_REPLICA_TARGET", "256"))
+    _REPLICA_TARGET = int(os.environ.get("SHINE_REPLICA_TARGET", "512"))
     _REPLICA_MAX = int(os.environ.get("SHINE_REPLICA_MAX", "32"))
 
     def _replicas_for(self, k: int, rows: int, n_points: int, device) -> tuple[int, torch.Tensor | None]:

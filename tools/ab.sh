@@ -1,2 +1,2 @@
-for r in 0 1 0 1; do echo "== fused replicas $r"; SHINE_FUSED_REPLICAS=$r timeout 200 python tools/kbench.py 2>/dev/null | grep -E "step 3xTF32"; done
-for t in 64 1024; do echo "== replicas target $t"; SHINE_REPLICA_TARGET=$t timeout 200 python tools/kbench.py 2>/dev/null | grep -E "step 3xTF32"; done
+echo "== big map"; timeout 200 python tools/kbench.py --frames 60 --step-m 3 --leaf-vox 0.05 --points 1048576 2>/dev/null | grep -E "table MB|step 3xTF32|infer 3x|query_|adam|zero"
+for t in 64 128 512 2048; do echo "== replica target $t"; SHINE_REPLICA_TARGET=$t timeout 200 python tools/kbench.py 2>/dev/null | grep -E "step 3xTF32"; done
