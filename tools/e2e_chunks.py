@@ -9,12 +9,12 @@ n = len(pool); c, l, w = pool.get_batch(n)
 ch, lh = c.cpu().pin_memory(), l.cpu().pin_memory()
 tr = SdfTrainer(cfg, octree, decoder)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-for chunks in (1, 2, 3, 4, 8):
-    for _ in range(3): tr.step_from_host(ch, lh, chunks=chunks)
+for chunks, graph in ((2, False), (2, True), (4, True), (8, True), (16, True)):
+    for _ in range(3): tr.step_from_host(ch, lh, chunks=chunks, use_graph=graph)
     ts = []
     for k in range(10):
-        flush.fill_(k); torch.cuda.synchronize(); t0 = time.perf_counter(); tr.step_from_host(ch, lh, chunks=chunks); ts.append(time.perf_counter() - t0)
-    ts.sort(); print(f"chunks {chunks}: median {ts[5]*1e3:.3f} ms  min {ts[0]*1e3:.3f} ms  -> {n/ts[5]/1e9:.2f} Gpts/s")
+        flush.fill_(k); torch.cuda.synchronize(); t0 = time.perf_counter(); tr.step_from_host(ch, lh, chunks=chunks, use_graph=graph); ts.append(time.perf_counter() - t0)
+    ts.sort(); print(f"chunks {chunks} graph={graph}: median {ts[5]*1e3:.3f} ms  min {ts[0]*1e3:.3f} ms  -> {n/ts[5]/1e9:.2f} Gpts/s")
 # raw H2D
 torch.cuda.synchronize(); d = torch.empty_like(c)
 t0 = time.perf_counter()
