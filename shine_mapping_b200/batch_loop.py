@@ -102,8 +102,9 @@ class _GraphedIteration:
             with torch.cuda.graph(self.graph):
                 self._body()
             self.lr = tr.lr
-            return        # the warm-up call above already did this iteration's work once... and capture does not run
+            return        # the warm-up call above did this iteration's work; capturing does not execute anything
         self.graph.replay()
+        tr.step_count += 1    # keep the host-side count in step with the device counter the replayed Adam uses
 
 
 def run_shine_mapping_batch(config: SHINEConfig, octree: FeatureOctree, decoder: Decoder, pool, iters=None,

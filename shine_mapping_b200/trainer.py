@@ -235,4 +235,6 @@ class SdfTrainer:
                 self._host_step_body(coord_h, label_h, weight_h, n, chunks, weighted, optimizer)
             self._host_graphs[key] = graph
         graph.replay()
+        if optimizer:
+            self.step_count += 1      # the replayed Adam advanced the device-side step counter
         return float(self.loss.item())
