@@ -36,12 +36,13 @@ def make_config(feat_levels=2, world_level=12, leaf_vox=0.2, device="cpu", **kw)
 
 
 def make_case(n_points=3000, n_batch=2048, feat_levels=2, seed=0, n_frames=1, poly=True, weighted=False,
-              reduction="mean", world_level=12, n_azimuth=None):
+              reduction="mean", world_level=12, n_azimuth=None, feature_dim=8):
     """Seeded synthetic case on the CPU: scans -> samples -> oracle octree -> batch (with out-of-map and
     out-of-cube stragglers appended to exercise the miss / clamp rules)."""
     from shine_mapping_b200 import synth
     torch.manual_seed(seed)
-    cfg = make_config(feat_levels, world_level, poly_int_on=poly, loss_weight_on=weighted, loss_reduction=reduction)
+    cfg = make_config(feat_levels, world_level, poly_int_on=poly, loss_weight_on=weighted, loss_reduction=reduction,
+                      feature_dim=feature_dim)
     gen = torch.Generator().manual_seed(seed)
     n_az = n_azimuth or max(8, n_points // 40)
     dirs = synth.lidar_directions(n_az)

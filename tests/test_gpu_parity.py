@@ -61,6 +61,18 @@ def test_unfused_class_surface_matches_oracle():
     print(compare_step(run_cuda_step(case, DEV, unfused=True), run_oracle_step(case)))
 
 
+@pytest.mark.parametrize("feature_dim", [4, 16])
+def test_class_surface_other_feature_dims(feature_dim):
+    """The generic query kernels take any feature_dim = 4*LP (here LP = 1 and 4); the fused decoder kernel is F=8 only
+    and must say so."""
+    from shine_mapping_b200 import _abi, sdf_bce_step
+    case = make_case(n_points=2000, n_batch=2000, feat_levels=3, seed=25, feature_dim=feature_dim)
+    print(compare_step(run_cuda_step(case, DEV, unfused=True), run_oracle_step(case)))
+    cfg, octree, dec = build_cuda_models(case, DEV)
+    with pytest.raises(_abi.ShineB200Error, match="feature_dim=8"):
+        sdf_bce_step(octree, dec, torch.from_numpy(case["coord"]).to(DEV), torch.from_numpy(case["label"]).to(DEV), 0.01)
+
+
 def test_plain_tf32_flag_is_close():
     case = make_case(n_points=2000, n_batch=2000, feat_levels=2, seed=23)
     got, want = run_cuda_step(case, DEV, tf32x1=True), run_oracle_step(case)
