@@ -248,6 +248,56 @@ __global__ void __launch_bounds__(256) query_fwd_kernel(const __grid_constant__ 
     *reinterpret_cast<float4*>(out + p * F + 4 * part) = acc;
 }
 
+
+// F = 8 specialisation of query_fwd: two adjacent lanes per point; lane `half` fetches the corners whose z bit is `half`
+// as whole 32-byte rows (LDG.256; slot ids are stored z-bit-major), so the pair's two loads of one instruction hit
+// z-neighbour rows = usually one 128-byte line; the partial blends are exchanged with one shfl per channel.
+__global__ void __launch_bounds__(256) query_fwd8_kernel(const __grid_constant__ shine_octree oct,
+                                                         const float* __restrict__ coord, int64_t n,
+                                                         float* __restrict__ out) {
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t p = gtid >> 1;
+    const int half = (int)(gtid & 1);
+    const bool valid = p < n;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (valid) { x = coord[3 * p]; y = coord[3 * p + 1]; z = coord[3 * p + 2]; }
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < oct.num_levels; ++i) {
+        const shine_level& lv = oct.lv[i];
+        const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
+        const int s = valid ? probe_slot(slots, lv.hash_capacity - 1, morton_of(x, y, z, lv.level)) : -1;
+        if (s < 0) continue;
+        const int4 id4 = ldg_i4(slots[s].ids + 4 * half);
+        float r0[8], r1[8], r2[8], r3[8];
+        ldg_row8(lv.features + (int64_t)id4.x * kF, r0);
+        ldg_row8(lv.features + (int64_t)id4.y * kF, r1);
+        ldg_row8(lv.features + (int64_t)id4.z * kF, r2);
+        ldg_row8(lv.features + (int64_t)id4.w * kF, r3);
+        Blend b; b.init(x, y, z, lv.level, oct.poly_interp != 0);
+        const float wz = half ? b.tz : b.uz;
+        const float w0 = __fmul_rn(__fmul_rn(b.ux, b.uy), wz), w1 = __fmul_rn(__fmul_rn(b.ux, b.ty), wz);
+        const float w2 = __fmul_rn(__fmul_rn(b.tx, b.uy), wz), w3 = __fmul_rn(__fmul_rn(b.tx, b.ty), wz);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            float a = acc[q];
+            a = fmaf(w0, r0[q], a); a = fmaf(w1, r1[q], a); a = fmaf(w2, r2[q], a); a = fmaf(w3, r3[q], a);
+            acc[q] = a;
+        }
+    }
+    float4 o;
+    {
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float send = half ? acc[q] : acc[4 + q];
+            const float recv = __shfl_xor_sync(kFull, send, 1);
+            v[q] = (half ? acc[4 + q] : acc[q]) + recv;
+        }
+        o = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    if (valid) *reinterpret_cast<float4*>(out + p * kF + 4 * half) = o;
+}
+
 template <int LP>
 __global__ void __launch_bounds__(256) query_bwd_kernel(const __grid_constant__ shine_octree oct,
                                                         const float* __restrict__ coord, int64_t n,
@@ -1519,6 +1569,7 @@ int launch_query(bool bwd, const shine_octree* oct, const float* coord, int64_t 
     const int64_t blocks = (threads + 255) / 256;
     if (blocks > INT32_MAX) return SHINE_ERR_UNSUPPORTED;
     if (bwd) query_bwd_kernel<LP><<<(unsigned)blocks, 256, 0, st>>>(*oct, coord, n, dfeat);
+    else if (LP == 2) query_fwd8_kernel<<<(unsigned)blocks, 256, 0, st>>>(*oct, coord, n, fwd_out);
     else query_fwd_kernel<LP><<<(unsigned)blocks, 256, 0, st>>>(*oct, coord, n, fwd_out);
     return (int)cudaGetLastError();
 }
