@@ -119,6 +119,54 @@ def make(name, feat_levels, n_frames, n_azimuth, n_batch, seed, poly=True, weigh
           f"-> {path} ({os.path.getsize(path) / 1e6:.2f} MB)")
 
 
+def make_eikonal(name, feat_levels, n_azimuth, n_batch, seed, poly=True, weight_e=0.1):
+    """Loop body with ekional_loss_on: the reference's get_gradient (utils/tools.py:175-185 — restated inline because
+    utils/tools.py imports open3d) on the reference's own FeatureOctree / Decoder, shine_batch.py:119-120,137-142,172-185."""
+    SHINEConfig, FeatureOctree, Decoder, dataSampler, sdf_bce_loss = import_reference()
+    sys.path.insert(0, ROOT)
+    from shine_mapping_b200 import synth
+    torch.manual_seed(seed)
+    cfg = reference_config(SHINEConfig, feat_levels, 0.2, poly, False, "mean")
+    octree, decoder, sampler = FeatureOctree(cfg), Decoder(cfg), dataSampler(cfg)
+    dirs, boxes = synth.lidar_directions(n_azimuth), synth.default_boxes()
+    origin = torch.zeros(3)
+    hits = synth.raycast_scene(origin, dirs, boxes, 3.0, 30.0)
+    coord, label, _, _, weight, _, _ = sampler.sample(hits * cfg.scale, origin * cfg.scale, None, None)
+    surface = coord[weight > 0, :]
+    octree.update(surface, False)
+    index = torch.randint(0, coord.shape[0], (n_batch,))
+    coord, label, weight = coord[index].clone(), label[index], weight[index]
+    sigma = cfg.logistic_gaussian_ratio * cfg.sigma_sigmoid_m * cfg.scale
+    tables_before = [p.detach().numpy().copy() for p in octree.hier_features]
+    coord.requires_grad_(True)                                             # shine_batch.py:119-120
+    feature = octree.query_feature(coord)
+    pred = decoder.sdf(feature)
+    surface_mask = weight > 0
+    g = torch.autograd.grad(outputs=pred, inputs=coord, grad_outputs=torch.ones_like(pred), create_graph=True,
+                            retain_graph=True, only_inputs=True)[0] * sigma   # get_gradient(coord, pred) * sigma_sigmoid
+    loss = sdf_bce_loss(pred, label, sigma, torch.abs(weight), False, "mean")
+    eikonal = ((1.0 - g[surface_mask].norm(2, dim=-1)) ** 2).mean()          # shine_batch.py:183-185
+    total = loss + weight_e * eikonal
+    total.backward()
+    out = {"cfg_json": np.array(json.dumps(dict(tree_level_world=12, tree_level_feat=feat_levels, feature_dim=cfg.feature_dim,
+                                                 poly_int_on=poly, leaf_vox_size=0.2, sigma=float(sigma), weighted=False,
+                                                 reduction="mean", decoder_frozen=False, n_frames=1, weight_e=weight_e))),
+           "frame_0": surface.numpy().copy(), "coord": coord.detach().numpy(), "label": label.numpy(), "weight": weight.numpy(),
+           "exp_g": g.detach().numpy(), "exp_eikonal": np.array(float(eikonal)), "exp_loss": np.array(float(total)),
+           "exp_pred": pred.detach().numpy()}
+    for k, t in enumerate(tables_before):
+        out[f"table_{k}"] = t
+        out[f"exp_tgrad_{k}"] = octree.hier_features[k].grad.numpy()
+    sd, params = decoder.state_dict(), dict(decoder.named_parameters())
+    for k in DEC_KEYS:
+        out["dec_" + k] = sd[k].numpy()
+        out["exp_dgrad_" + k] = params[k].grad.numpy()
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: N={coord.shape[0]} eikonal={float(eikonal):.6f} loss={float(total):.6f} -> {path} "
+          f"({os.path.getsize(path) / 1e6:.2f} MB)")
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         sys.exit(f"{REF} not found: goldens can only be minted where the reference is mounted")
@@ -127,3 +175,4 @@ if __name__ == "__main__":
          pretrained=True)
     make("ref_incre_l3_sum_weighted_linear", feat_levels=3, n_frames=2, n_azimuth=10, n_batch=1200, seed=44,
          poly=False, weighted=True, reduction="sum")
+    make_eikonal("ref_eikonal_l3", feat_levels=3, n_azimuth=10, n_batch=1000, seed=45)

@@ -168,6 +168,34 @@ def test_eikonal_through_class_surface_matches_oracle(levels, poly):
         assert np.abs(p.grad.cpu().numpy() - gt).max() <= 1e-3 * np.abs(gt).max() + 1e-9, name
 
 
+def test_eikonal_matches_reference_golden():
+    """The CUDA eikonal path against the outputs of the reference's own classes (tests/golden/ref_eikonal_l3.npz)."""
+    import json
+    import os
+    from shine_mapping_b200 import SdfTrainer
+    from shine_mapping_b200.batch_loop import eikonal_iteration
+    from tests.parity_utils import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "ref_eikonal_l3.npz"))
+    cfg_j = json.loads(str(z["cfg_json"]))
+    case = {"cfg": cfg_j, "frames": [z["frame_0"]], "tables": [z[f"table_{k}"] for k in range(cfg_j["tree_level_feat"])],
+            "dec": {k: z["dec_" + k] for k in DEC_KEYS}, "coord": z["coord"], "label": z["label"], "weight": z["weight"]}
+    cfg, octree, dec = build_cuda_models(case, DEV)
+    cfg.ekional_loss_on, cfg.weight_e = True, cfg_j["weight_e"]
+    tr = SdfTrainer(cfg, octree, dec)
+    tr.zero_grad()
+    total, eik, g = eikonal_iteration(cfg, octree, dec, tr, torch.from_numpy(z["coord"]).to(DEV),
+                                      torch.from_numpy(z["label"]).to(DEV), torch.from_numpy(z["weight"]).to(DEV))
+    assert np.abs(g.cpu().numpy() - z["exp_g"]).max() <= 1e-4 * np.abs(z["exp_g"]).max() + 1e-7
+    assert abs(float(eik) - float(z["exp_eikonal"])) <= 1e-4 * abs(float(z["exp_eikonal"]))
+    assert abs(float(total) - float(z["exp_loss"])) <= 1e-4 * abs(float(z["exp_loss"]))
+    for k in range(cfg_j["tree_level_feat"]):
+        want = z[f"exp_tgrad_{k}"]
+        assert np.abs(tr.table_grads[k].cpu().numpy() - want)[:-1].max() <= 1e-3 * np.abs(want).max() + 1e-9
+    for name, p in zip(DEC_KEYS, dec.fused_params()):
+        want = z["exp_dgrad_" + name]
+        assert np.abs(p.grad.cpu().numpy() - want).max() <= 1e-3 * np.abs(want).max() + 1e-9
+
+
 def test_points_to_morton_bit_exact():
     from shine_mapping_b200 import _abi
     from oracle import shine_oracle as orc

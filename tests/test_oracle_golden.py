@@ -81,3 +81,27 @@ def test_unseen_voxel_gives_zero_feature_and_mlp_of_zero():
 def test_raises_without_featured_level():
     with pytest.raises(ValueError):
         orc.OracleOctree(12, 0)
+
+
+def test_oracle_eikonal_matches_reference_golden():
+    """ekional_loss_on: d pred / d coord with create_graph=True on the reference's own classes (golden minted by
+    oracle/make_golden.py::make_eikonal) vs the oracle's train_step_eikonal."""
+    import json
+    import os
+    from tests.parity_utils import DEC_KEYS, GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "ref_eikonal_l3.npz"))
+    cfg = json.loads(str(z["cfg_json"]))
+    case = {"cfg": cfg, "frames": [z["frame_0"]], "tables": [z[f"table_{k}"] for k in range(cfg["tree_level_feat"])],
+            "dec": {k: z["dec_" + k] for k in DEC_KEYS}, "coord": z["coord"], "label": z["label"], "weight": z["weight"]}
+    o, dec = oracle_from_case(case)
+    got = orc.train_step_eikonal(o, dec, torch.from_numpy(z["coord"]), torch.from_numpy(z["label"]),
+                                 torch.from_numpy(z["weight"]), cfg["sigma"], cfg["weight_e"])
+    assert np.abs(got["g"].numpy() - z["exp_g"]).max() <= 1e-5 * np.abs(z["exp_g"]).max()
+    assert abs(float(got["eikonal"]) - float(z["exp_eikonal"])) <= 1e-5 * abs(float(z["exp_eikonal"]))
+    assert abs(float(got["loss"]) - float(z["exp_loss"])) <= 1e-6 * abs(float(z["exp_loss"]))
+    for k, g in enumerate(got["table_grads"]):
+        want = z[f"exp_tgrad_{k}"]
+        assert np.abs(g.numpy() - want).max() <= 1e-4 * np.abs(want).max() + 1e-12
+    for k in DEC_KEYS:
+        want = z["exp_dgrad_" + k]
+        assert np.abs(got["dec_grads"][k].numpy() - want).max() <= 1e-4 * np.abs(want).max() + 1e-12
