@@ -261,6 +261,22 @@ class FeatureOctree(nn.Module):
         state["_levels"] = levels
         return state
 
+    def _apply(self, fn, *args, **kwargs):
+        """`.to()/.cuda()/.cpu()`: move the per-level index arrays together with the parameters; device hash tables,
+        replica scratch and cached descriptors are rebuilt on demand."""
+        super()._apply(fn, *args, **kwargs)
+        for st in self._levels:
+            for name in ("node_keys", "node_ids", "node_keys_sorted", "corner_lex_sorted", "corner_rows_sorted",
+                         "corner_morton_by_row"):
+                setattr(st, name, fn(getattr(st, name)))
+            st.hash, st.hash_capacity, st.hash_count = None, 0, 0
+        self.importance_weight = [fn(t) for t in self.importance_weight]
+        self.features_last_frame = [fn(t) for t in self.features_last_frame]
+        self._grad_scratch, self._desc_cache, self._last_coord, self._hier_idx = {}, None, None, []
+        if len(self.hier_features):
+            self.device = self.hier_features[0].device
+        return self
+
     # ---- reference API -------------------------------------------------------------------------------------
 
     def set_zero(self):

@@ -112,6 +112,20 @@ def test_octree_pickles_like_the_reference_checkpoint():
     assert torch.equal(clone.hier_features[0], o.hier_features[0])
 
 
+def test_module_to_moves_the_whole_structure():
+    """`.to()` must carry the index arrays along with hier_features (checkpoints loaded with map_location)."""
+    from shine_mapping_b200 import FeatureOctree
+    case = make_case(n_points=600, n_batch=10, feat_levels=2, seed=4)
+    o = FeatureOctree(make_config(2, device="cpu"))
+    o.update(torch.from_numpy(case["frames"][0]))
+    before = o.nodes_lookup_tables[12]
+    o2 = o.to(torch.float32).cpu()          # dtype/device fns pass through integer arrays unchanged
+    assert o2 is o and o.nodes_lookup_tables[12] == before
+    assert o._levels[12].node_keys.dtype == torch.int64 and o._levels[12].node_ids.dtype == torch.int32
+    o.update(torch.from_numpy(case["frames"][0]) + 0.01)     # still consistent after the move
+    assert len(o.nodes_lookup_tables[12]) >= len(before)
+
+
 def test_query_on_cpu_fails_loudly_no_fallback():
     from shine_mapping_b200 import Decoder, FeatureOctree, _abi, sdf_bce_step
     case = make_case(n_points=600, n_batch=10, feat_levels=2, seed=4)
