@@ -12,7 +12,9 @@
  *   - return 0 on success, a positive cudaError_t on a CUDA failure, a negative SHINE_ERR_* on a bad
  *     argument / unsupported configuration.  shine_error_string() decodes either.
  *   - all buffers are caller-owned device memory; nothing is allocated, freed or synchronised inside;
- *     every call is asynchronous on `stream` and re-entrant.
+ *     every call is asynchronous on `stream` and re-entrant.  Kernels are launched on the device that owns the
+ *     buffers (looked up from the pointers), whatever the calling thread's current device is; a batch on another
+ *     device than the tables is SHINE_ERR_INVALID_ARG (pinned host batch pointers are accepted).
  *   - levels are described BOTTOM-UP like `FeatureOctree.hierarchical_indices`
  *     (model/feature_octree.py:201-202): lv[0] is the leaf level `tree_level_world`.
  *   - a voxel that is not in the level's node table is a MISS: its eight corner ids are -1, its feature
@@ -28,7 +30,7 @@
 extern "C" {
 #endif
 
-#define SHINE_ABI_VERSION 1
+#define SHINE_ABI_VERSION 2
 #define SHINE_MAX_LEVELS 8
 #define SHINE_HASH_SLOT_BYTES 64
 
@@ -84,9 +86,11 @@ const char* shine_error_string(int code);
 
 /* Build / extend the device node table of one level.  Replaces the Python dict fill at
  * model/feature_octree.py:162-166.  `slots` must have been memset to 0xFF (empty) before the first
- * insert.  keys: [n] int64 Morton codes, corner_ids: [n,8] int32 rows, node_base: ordinal of keys[0]. */
+ * insert.  keys: [n] int64 Morton codes, corner_ids: [n,8] int32 rows, node_base: ordinal of keys[0].
+ * overflow_count (device int32, may be NULL): incremented once per key that could NOT be stored because the
+ * table is full — a Python dict never drops a key, so the caller must grow the table and re-insert. */
 int shine_hash_insert(void* slots, uint32_t capacity, const int64_t* keys, const int32_t* corner_ids,
-                      int64_t n, int32_t node_base, void* stream);
+                      int64_t n, int32_t node_base, int32_t* overflow_count, void* stream);
 
 /* kal.ops.spc.quantize_points + points_to_morton (call sites model/feature_octree.py:203-204):
  * coord [n,3] fp32 -> morton [n] int64 at `level`. */

@@ -13,6 +13,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SHINE_B200_LIB") or os.path.join(_HERE, "csrc", "libshine_b200.so")
 
+ABI_VERSION = 2
 MAX_LEVELS = 8
 HASH_SLOT_BYTES = 64
 ADAM_MAX_TENSORS = 16
@@ -52,7 +53,7 @@ _OCT, _DEC = C.POINTER(ShineOctree), C.POINTER(ShineDecoder)
 SYMBOLS = {
     "shine_abi_version": (C.c_int, []),
     "shine_error_string": (C.c_char_p, [C.c_int]),
-    "shine_hash_insert": (C.c_int, [_vp, _u32, _vp, _vp, _i64, _i32, _vp]),
+    "shine_hash_insert": (C.c_int, [_vp, _u32, _vp, _vp, _i64, _i32, _vp, _vp]),
     "shine_points_to_morton": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "shine_get_indices": (C.c_int, [_OCT, _vp, _i64, _vp, _vp]),
     "shine_query_fwd": (C.c_int, [_OCT, _vp, _i64, _vp, _vp]),
@@ -87,7 +88,7 @@ def lib() -> C.CDLL:
         for name, (restype, argtypes) in SYMBOLS.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = restype, argtypes
-        if handle.shine_abi_version() != 1:
+        if handle.shine_abi_version() != ABI_VERSION:
             raise ShineB200Error("libshine_b200.so ABI version mismatch; rebuild")
         _lib = handle
     return _lib

@@ -92,6 +92,7 @@ class _GraphedIteration:
         tr = self.trainer
         if self.graph is None or self.lr != tr.lr:
             dev = tr.flat_grad.device
+            tr._sync_adam_state()             # other paths (train_step, eikonal loop) count on the host only
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):     # warm-up outside capture (lazy inits, allocator)

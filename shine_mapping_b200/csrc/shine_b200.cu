@@ -32,137 +32,17 @@
 #define SHINE_INFER_MINB 3
 #endif
 
+#include "shine_device.cuh"
+
 namespace {
-
-// ------------------------------------------------------------------------------------------------------
-// constants / small helpers
-// ------------------------------------------------------------------------------------------------------
-
-constexpr int kTile = 16;          // points per warp tile
-constexpr int kF = 8;              // fused path: feature_dim
-constexpr int kH = 32;             // fused path: hidden width
-constexpr int kWS = 40;            // padded row stride (floats) of 32-wide smem matrices: conflict-free frags
-constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
-constexpr unsigned kFull = 0xFFFFFFFFu;
-
-struct __align__(64) HashSlot {
-    unsigned long long key;   // Morton code of the voxel, kEmptyKey when free
-    int32_t node;             // insertion ordinal (diagnostics)
-    int32_t pad[5];
-    int32_t ids[8];           // rows of the 8 corners, stored z-bit-major: [c0 c2 c4 c6 | c1 c3 c5 c7] (second sector)
-};
-static_assert(sizeof(HashSlot) == SHINE_HASH_SLOT_BYTES, "slot must be 64 bytes");
-
-// 64-bit mix (two multiplies).  A cheaper 32-bit fmix32 of the folded key was measured and rejected: more first-probe
-// collisions (gather-only kernel 0.111 -> 0.137 ms).
-__host__ __device__ __forceinline__ uint32_t hash_key(unsigned long long k) {
-    k ^= k >> 31; k *= 0x9E3779B97F4A7C15ull;
-    k ^= k >> 29; k *= 0xBF58476D1CE4E5B9ull;
-    k ^= k >> 32;
-    return (uint32_t)k;
-}
-
-// bit i of v -> bit 3i (16 significant bits, as kaolin's int16 coordinates)
-__device__ __forceinline__ unsigned long long spread3(uint32_t v) {
-    unsigned long long x = v & 0xFFFFull;
-    x = (x | (x << 16)) & 0x0000FF0000FFull;
-    x = (x | (x << 8)) & 0x00F00F00F00Full;
-    x = (x | (x << 4)) & 0x0C30C30C30C3ull;
-    x = (x | (x << 2)) & 0x249249249249ull;
-    return x;
-}
-
-// kal.ops.spc.quantize_points (model/feature_octree.py:203): floor(clamp(res*(x+1)/2, 0, res-1)), fp32 op order kept
-__device__ __forceinline__ uint32_t quantize1(float x, float res) {
-    float v = __fmul_rn(__fmul_rn(res, __fadd_rn(x, 1.0f)), 0.5f);
-    v = fminf(fmaxf(v, 0.0f), res - 1.0f);
-    return (uint32_t)(int)floorf(v);
-}
-
-// kal.ops.spc.points_to_morton (model/feature_octree.py:204): x -> bit 3i+2, y -> 3i+1, z -> 3i
-__device__ __forceinline__ unsigned long long morton_of(float x, float y, float z, int level) {
-    const float res = (float)(1u << level);
-    return (spread3(quantize1(x, res)) << 2) | (spread3(quantize1(y, res)) << 1) | spread3(quantize1(z, res));
-}
-
-// FeatureOctree.interpolat (model/feature_octree.py:172-185): per-axis blend factor at `level`
-__device__ __forceinline__ float axis_t(float x, float res, bool poly) {
-    const float c = __fmul_rn(res, __fmaf_rn(x, 0.5f, 0.5f));   // x*0.5 is exact, so the fma rounds like mul+add
-    const float d = c - truncf(c);                              // torch.frac
-    if (!poly) return d;
-    const float d2 = __fmul_rn(d, d);
-    const float d3 = __fmul_rn(d2, d);
-    return __fsub_rn(__fmul_rn(3.0f, d2), __fmul_rn(2.0f, d3));
-}
-
-struct Blend {   // the 8 weights of model/feature_octree.py:186-193, corner c = (x bit2, y bit1, z bit0)
-    float tx, ty, tz, ux, uy, uz;
-    __device__ __forceinline__ void init(float x, float y, float z, int level, bool poly) {
-        const float res = (float)(1u << level);
-        tx = axis_t(x, res, poly); ty = axis_t(y, res, poly); tz = axis_t(z, res, poly);
-        ux = __fsub_rn(1.0f, tx); uy = __fsub_rn(1.0f, ty); uz = __fsub_rn(1.0f, tz);
-    }
-    __device__ __forceinline__ float w(int c) const {
-        const float a = (c & 4) ? tx : ux, b = (c & 2) ? ty : uy, d = (c & 1) ? tz : uz;
-        return __fmul_rn(__fmul_rn(a, b), d);
-    }
-};
-
-__device__ __forceinline__ float4 ldg_f4(const float* p) {
-    return __ldg(reinterpret_cast<const float4*>(p));
-}
-// one instruction per full 32-byte feature row (sm_100a LDG.E.ENL2.256)
-__device__ __forceinline__ void ldg_row8(const float* p, float (&v)[8]) {
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
-                 : "l"(p));
-}
-__device__ __forceinline__ int4 ldg_i4(const int32_t* p) {
-    return __ldg(reinterpret_cast<const int4*>(p));
-}
-__device__ __forceinline__ void red_add_f4(float* p, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-// gradient privatisation: replica 0 is the caller's grad table, replicas 1.. live in lv.grad_replicas
-__device__ __forceinline__ float* grad_base(const shine_level& lv, uint32_t warp_id, int F) {
-    const uint32_t r = lv.num_replicas > 1 ? (warp_id & (uint32_t)(lv.num_replicas - 1)) : 0u;
-    return r == 0 ? lv.feature_grads : lv.grad_replicas + (size_t)(r - 1) * (size_t)lv.rows * F;
-}
-
-// nodes_lookup_tables[level].get(morton, [-1]*8)  (model/feature_octree.py:205-209) as an open-addressing probe.
-// Returns the slot index or -1.  The first probe loads key speculatively together with the caller's id loads.
-__device__ __forceinline__ int probe_slot(const HashSlot* __restrict__ slots, uint32_t mask, unsigned long long key) {
-    uint32_t h = hash_key(key) & mask;
-#pragma unroll 1
-    for (uint32_t n = 0; n <= mask; ++n) {
-        const unsigned long long k = __ldg(&slots[h].key);
-        if (k == key) return (int)h;
-        if (k == kEmptyKey) return -1;
-        h = (h + 1) & mask;
-    }
-    return -1;
-}
-
-__device__ __noinline__ int probe_slot_from(const HashSlot* __restrict__ slots, uint32_t mask, unsigned long long key,
-                                            uint32_t start) {
-    uint32_t h = start & mask;
-#pragma unroll 1
-    for (uint32_t n = 0; n < mask; ++n) {
-        const unsigned long long k = __ldg(&slots[h].key);
-        if (k == key) return (int)h;
-        if (k == kEmptyKey) return -1;
-        h = (h + 1) & mask;
-    }
-    return -1;
-}
 
 // ------------------------------------------------------------------------------------------------------
 // hash build (model/feature_octree.py:162-166)
 // ------------------------------------------------------------------------------------------------------
 
 __global__ void hash_insert_kernel(HashSlot* __restrict__ slots, uint32_t mask, const int64_t* __restrict__ keys,
-                                   const int32_t* __restrict__ corner_ids, int64_t n, int32_t node_base) {
+                                   const int32_t* __restrict__ corner_ids, int64_t n, int32_t node_base,
+                                   int32_t* __restrict__ overflow) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long key = (unsigned long long)keys[i];
@@ -177,6 +57,7 @@ __global__ void hash_insert_kernel(HashSlot* __restrict__ slots, uint32_t mask, 
         }
         h = (h + 1) & mask;
     }
+    if (overflow) atomicAdd(overflow, 1);   // table full: the key was NOT stored — the caller must grow the table
 }
 
 __global__ void points_to_morton_kernel(const float* __restrict__ coord, int64_t n, int level,
@@ -1443,23 +1324,6 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamP
 // host side
 // ------------------------------------------------------------------------------------------------------
 
-inline bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
-
-int check_octree(const shine_octree* o, bool need_grads) {
-    if (!o) return SHINE_ERR_INVALID_ARG;
-    if (o->num_levels < 1 || o->num_levels > SHINE_MAX_LEVELS) return SHINE_ERR_INVALID_ARG;
-    if (o->feature_dim < 4 || (o->feature_dim & 3)) return SHINE_ERR_UNSUPPORTED;
-    for (int i = 0; i < o->num_levels; ++i) {
-        const shine_level& lv = o->lv[i];
-        if (!lv.hash_slots || !lv.features || !is_pow2(lv.hash_capacity) || lv.rows < 1) return SHINE_ERR_INVALID_ARG;
-        if (lv.level < 1 || lv.level > 16) return SHINE_ERR_INVALID_ARG;
-        if (need_grads && !lv.feature_grads) return SHINE_ERR_INVALID_ARG;
-        if (lv.num_replicas > 1 && (!is_pow2((uint32_t)lv.num_replicas) || lv.num_replicas > 64 || !lv.grad_replicas))
-            return SHINE_ERR_INVALID_ARG;
-    }
-    return SHINE_OK;
-}
-
 int check_decoder(const shine_decoder* d, const shine_octree* o) {
     if (!d) return SHINE_ERR_INVALID_ARG;
     if (d->in_dim != kF || d->hidden != kH || d->mlp_level != 2 || o->feature_dim != kF) return SHINE_ERR_UNSUPPORTED;
@@ -1467,24 +1331,13 @@ int check_decoder(const shine_decoder* d, const shine_octree* o) {
     return SHINE_OK;
 }
 
-int sm_count() {
-    static int cached[64] = {0};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
-    if (cached[dev] == 0) {
-        int n = 0;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-        cached[dev] = n;
-    }
-    return cached[dev];
-}
-
 template <int NTF, bool TRAIN, bool DEC_GRAD, int LMAX>
 int launch_fused_t(const StepParams& P, cudaStream_t st) {
     auto kern = sdf_fused_kernel<NTF, TRAIN, DEC_GRAD, LMAX>;
     const int smem_floats = SmemPlan::STAGE + (DEC_GRAD ? 8 * SmemPlan::kStagePerWarp : 0);
     const size_t smem_bytes = (size_t)smem_floats * sizeof(float);
-    static int per_sm_cached = 0;   // per template instantiation; one process drives one GPU
+    static int per_sm_by_dev[kMaxDevices] = {0};   // per template instantiation AND per device: the >48 KB dynamic
+    int& per_sm_cached = per_sm_by_dev[current_device()];   // shared-memory opt-in is a per-device function attribute
     cudaError_t e;
     if (per_sm_cached == 0) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
@@ -1526,7 +1379,8 @@ int launch_fused(const StepParams& P, uint32_t flags, cudaStream_t st) {
 template <int LMAX>
 int launch_infer_tc_t(const StepParams& P, cudaStream_t st) {
     auto kern = sdf_infer_tc_kernel<LMAX>;
-    static int per_sm_cached = 0;
+    static int per_sm_by_dev[kMaxDevices] = {0};
+    int& per_sm_cached = per_sm_by_dev[current_device()];
     if (per_sm_cached == 0) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TcPlan::BYTES);
         if (e != cudaSuccess) return (int)e;
@@ -1620,18 +1474,21 @@ const char* shine_error_string(int code) {
 }
 
 int shine_hash_insert(void* slots, uint32_t capacity, const int64_t* keys, const int32_t* corner_ids, int64_t n,
-                      int32_t node_base, void* stream) {
+                      int32_t node_base, int32_t* overflow_count, void* stream) {
     if (!slots || !is_pow2(capacity) || n < 0 || (n > 0 && (!keys || !corner_ids))) return SHINE_ERR_INVALID_ARG;
     if (n == 0) return SHINE_OK;
+    DeviceGuard guard(slots);
     const int64_t blocks = (n + 255) / 256;
     hash_insert_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<HashSlot*>(slots),
-                                                                          capacity - 1, keys, corner_ids, n, node_base);
+                                                                          capacity - 1, keys, corner_ids, n, node_base,
+                                                                          overflow_count);
     return (int)cudaGetLastError();
 }
 
 int shine_points_to_morton(const float* coord, int64_t n, int32_t level, int64_t* morton, void* stream) {
     if (n < 0 || level < 1 || level > 16 || (n > 0 && (!coord || !morton))) return SHINE_ERR_INVALID_ARG;
     if (n == 0) return SHINE_OK;
+    DeviceGuard guard(morton);
     points_to_morton_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(coord, n, level, morton);
     return (int)cudaGetLastError();
 }
@@ -1641,6 +1498,8 @@ int shine_get_indices(const shine_octree* oct, const float* coord, int64_t n, in
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!coord || !out_idx))) return SHINE_ERR_INVALID_ARG;
     if (n == 0) return SHINE_OK;
+    if ((rc = check_same_device(oct, coord))) return rc;
+    DeviceGuard guard(oct->lv[0].features);
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)oct->num_levels);
     get_indices_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*oct, coord, n, out_idx);
     return (int)cudaGetLastError();
@@ -1651,6 +1510,8 @@ int shine_query_fwd(const shine_octree* oct, const float* coord, int64_t n, floa
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!coord || !out_feat))) return SHINE_ERR_INVALID_ARG;
     if (n == 0) return SHINE_OK;
+    if ((rc = check_same_device(oct, coord))) return rc;
+    DeviceGuard guard(oct->lv[0].features);
     return dispatch_query(false, oct, coord, n, out_feat, nullptr, (cudaStream_t)stream);
 }
 
@@ -1659,6 +1520,8 @@ int shine_query_bwd(const shine_octree* oct, const float* coord, int64_t n, cons
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!coord || !dfeat))) return SHINE_ERR_INVALID_ARG;
     if (n == 0) return SHINE_OK;
+    if ((rc = check_same_device(oct, coord))) return rc;
+    DeviceGuard guard(oct->lv[0].features);
     return dispatch_query(true, oct, coord, n, nullptr, dfeat, (cudaStream_t)stream);
 }
 
@@ -1668,6 +1531,8 @@ int shine_query_coord_grad(const shine_octree* oct, const float* coord, int64_t 
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!coord || !dfeat || !out_dcoord))) return SHINE_ERR_INVALID_ARG;
     if (n == 0) return SHINE_OK;
+    if ((rc = check_same_device(oct, coord))) return rc;
+    DeviceGuard guard(oct->lv[0].features);
     return dispatch_tangent<0>(oct, coord, n, dfeat, nullptr, out_dcoord, (cudaStream_t)stream);
 }
 
@@ -1677,6 +1542,8 @@ int shine_query_tangent_fwd(const shine_octree* oct, const float* coord, int64_t
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!coord || !tangent || !out_feat))) return SHINE_ERR_INVALID_ARG;
     if (n == 0) return SHINE_OK;
+    if ((rc = check_same_device(oct, coord))) return rc;
+    DeviceGuard guard(oct->lv[0].features);
     return dispatch_tangent<1>(oct, coord, n, nullptr, tangent, out_feat, (cudaStream_t)stream);
 }
 
@@ -1686,6 +1553,8 @@ int shine_query_tangent_bwd(const shine_octree* oct, const float* coord, int64_t
     if (rc) return rc;
     if (n < 0 || (n > 0 && (!coord || !tangent || !dfeat))) return SHINE_ERR_INVALID_ARG;
     if (n == 0) return SHINE_OK;
+    if ((rc = check_same_device(oct, coord))) return rc;
+    DeviceGuard guard(oct->lv[0].features);
     return dispatch_tangent<2>(oct, coord, n, dfeat, tangent, nullptr, (cudaStream_t)stream);
 }
 
@@ -1701,6 +1570,8 @@ int shine_sdf_infer(const shine_octree* oct, const shine_decoder* dec, const flo
     rc = fill_params(P, oct, dec, coord, n);
     if (rc) return rc;
     if (n == 0) return SHINE_OK;
+    if ((rc = check_same_device(oct, coord))) return rc;
+    DeviceGuard guard(oct->lv[0].features);
     P.pred = out_pred; P.mask = out_mask; P.mask_level = mask_level;
     if (flags & SHINE_FLAG_TCGEN05) return launch_infer_tc(P, (cudaStream_t)stream);
     return launch_fused<false, false>(P, flags, (cudaStream_t)stream);
@@ -1720,6 +1591,8 @@ int shine_sdf_bce_fwd(const shine_octree* oct, const shine_decoder* dec, const f
     rc = fill_params(P, oct, dec, coord, n);
     if (rc) return rc;
     if (n == 0) return SHINE_OK;
+    if ((rc = check_same_device(oct, coord))) return rc;
+    DeviceGuard guard(oct->lv[0].features);
     P.label = label; P.weight = weight; P.weighted = (flags & SHINE_FLAG_WEIGHTED) ? 1 : 0;
     P.sigma = sigma; P.loss_scale = loss_scale; P.pred = out_pred; P.loss = out_loss;
     return launch_fused<false, false>(P, flags, (cudaStream_t)stream);
@@ -1741,6 +1614,8 @@ int shine_sdf_bce_step(const shine_octree* oct, const shine_decoder* dec, const 
     rc = fill_params(P, oct, dec, coord, n);
     if (rc) return rc;
     if (n == 0) return SHINE_OK;
+    if ((rc = check_same_device(oct, coord))) return rc;
+    DeviceGuard guard(oct->lv[0].features);
     P.label = label; P.weight = weight; P.weighted = (flags & SHINE_FLAG_WEIGHTED) ? 1 : 0;
     P.sigma = sigma; P.loss_scale = loss_scale; P.d_loss = d_loss; P.pred = out_pred; P.loss = out_loss;
     return dec_grad ? launch_fused<true, true>(P, flags, (cudaStream_t)stream)
@@ -1757,6 +1632,7 @@ int shine_reduce_grad_replicas(const shine_octree* oct, void* stream) {
             if (n4 > max_n4) max_n4 = n4;
         }
     if (max_n4 == 0) return SHINE_OK;
+    DeviceGuard guard(oct->lv[0].features);
     int64_t blocks = (max_n4 + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 8;
     if (blocks > cap) blocks = cap;
@@ -1768,6 +1644,7 @@ int shine_reduce_grad_replicas(const shine_octree* oct, void* stream) {
 static int adam_launch(const shine_adam_tensor* tensors, int32_t count, float beta1, float beta2, float eps, int32_t step,
                        const float* bc_dev, int32_t zero_grad, cudaStream_t st) {
     AdamParams A;
+    DeviceGuard guard(tensors[0].param);
     int64_t max_n = 0;
     for (int i = 0; i < count; ++i) {
         const shine_adam_tensor& t = tensors[i];
@@ -1800,6 +1677,7 @@ int shine_adam_step_dev(const shine_adam_tensor* tensors, int32_t count, float b
                         void* state, int32_t zero_grad, void* stream) {
     if (!tensors || count < 1 || count > SHINE_ADAM_MAX_TENSORS || !state) return SHINE_ERR_INVALID_ARG;
     AdamDevState* st = reinterpret_cast<AdamDevState*>(state);
+    DeviceGuard guard(state);
     adam_bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(st, beta1, beta2);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int)e;

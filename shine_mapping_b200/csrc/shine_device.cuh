@@ -1,0 +1,214 @@
+// shine_device.cuh — device helpers shared by every translation unit of libshine_b200.so: the hash-slot format,
+// Morton / quantise / interpolation arithmetic of the reference (model/feature_octree.py:172-218) and small PTX wrappers.
+// Everything lives in an anonymous namespace (one private copy per .cu file).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "shine_b200.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------
+// constants / small helpers
+// ------------------------------------------------------------------------------------------------------
+
+constexpr int kTile = 16;          // points per warp tile
+constexpr int kF = 8;              // fused path: feature_dim
+constexpr int kH = 32;             // fused path: hidden width
+constexpr int kWS = 40;            // padded row stride (floats) of 32-wide smem matrices: conflict-free frags
+constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+constexpr unsigned kFull = 0xFFFFFFFFu;
+
+struct __align__(64) HashSlot {
+    unsigned long long key;   // Morton code of the voxel, kEmptyKey when free
+    int32_t node;             // insertion ordinal (diagnostics)
+    int32_t pad[5];
+    int32_t ids[8];           // rows of the 8 corners, stored z-bit-major: [c0 c2 c4 c6 | c1 c3 c5 c7] (second sector)
+};
+static_assert(sizeof(HashSlot) == SHINE_HASH_SLOT_BYTES, "slot must be 64 bytes");
+
+// 64-bit mix (two multiplies).  A cheaper 32-bit fmix32 of the folded key was measured and rejected: more first-probe
+// collisions (gather-only kernel 0.111 -> 0.137 ms).
+__host__ __device__ __forceinline__ uint32_t hash_key(unsigned long long k) {
+    k ^= k >> 31; k *= 0x9E3779B97F4A7C15ull;
+    k ^= k >> 29; k *= 0xBF58476D1CE4E5B9ull;
+    k ^= k >> 32;
+    return (uint32_t)k;
+}
+
+// bit i of v -> bit 3i (16 significant bits, as kaolin's int16 coordinates)
+__device__ __forceinline__ unsigned long long spread3(uint32_t v) {
+    unsigned long long x = v & 0xFFFFull;
+    x = (x | (x << 16)) & 0x0000FF0000FFull;
+    x = (x | (x << 8)) & 0x00F00F00F00Full;
+    x = (x | (x << 4)) & 0x0C30C30C30C3ull;
+    x = (x | (x << 2)) & 0x249249249249ull;
+    return x;
+}
+
+// kal.ops.spc.quantize_points (model/feature_octree.py:203): floor(clamp(res*(x+1)/2, 0, res-1)), fp32 op order kept
+__device__ __forceinline__ uint32_t quantize1(float x, float res) {
+    float v = __fmul_rn(__fmul_rn(res, __fadd_rn(x, 1.0f)), 0.5f);
+    v = fminf(fmaxf(v, 0.0f), res - 1.0f);
+    return (uint32_t)(int)floorf(v);
+}
+
+// kal.ops.spc.points_to_morton (model/feature_octree.py:204): x -> bit 3i+2, y -> 3i+1, z -> 3i
+__device__ __forceinline__ unsigned long long morton_of(float x, float y, float z, int level) {
+    const float res = (float)(1u << level);
+    return (spread3(quantize1(x, res)) << 2) | (spread3(quantize1(y, res)) << 1) | spread3(quantize1(z, res));
+}
+
+// FeatureOctree.interpolat (model/feature_octree.py:172-185): per-axis blend factor at `level`
+__device__ __forceinline__ float axis_t(float x, float res, bool poly) {
+    const float c = __fmul_rn(res, __fmaf_rn(x, 0.5f, 0.5f));   // x*0.5 is exact, so the fma rounds like mul+add
+    const float d = c - truncf(c);                              // torch.frac
+    if (!poly) return d;
+    const float d2 = __fmul_rn(d, d);
+    const float d3 = __fmul_rn(d2, d);
+    return __fsub_rn(__fmul_rn(3.0f, d2), __fmul_rn(2.0f, d3));
+}
+
+struct Blend {   // the 8 weights of model/feature_octree.py:186-193, corner c = (x bit2, y bit1, z bit0)
+    float tx, ty, tz, ux, uy, uz;
+    __device__ __forceinline__ void init(float x, float y, float z, int level, bool poly) {
+        const float res = (float)(1u << level);
+        tx = axis_t(x, res, poly); ty = axis_t(y, res, poly); tz = axis_t(z, res, poly);
+        ux = __fsub_rn(1.0f, tx); uy = __fsub_rn(1.0f, ty); uz = __fsub_rn(1.0f, tz);
+    }
+    __device__ __forceinline__ float w(int c) const {
+        const float a = (c & 4) ? tx : ux, b = (c & 2) ? ty : uy, d = (c & 1) ? tz : uz;
+        return __fmul_rn(__fmul_rn(a, b), d);
+    }
+};
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+// one instruction per full 32-byte feature row (sm_100a LDG.E.ENL2.256)
+__device__ __forceinline__ void ldg_row8(const float* p, float (&v)[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ int4 ldg_i4(const int32_t* p) {
+    return __ldg(reinterpret_cast<const int4*>(p));
+}
+__device__ __forceinline__ void red_add_f4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// gradient privatisation: replica 0 is the caller's grad table, replicas 1.. live in lv.grad_replicas
+__device__ __forceinline__ float* grad_base(const shine_level& lv, uint32_t warp_id, int F) {
+    const uint32_t r = lv.num_replicas > 1 ? (warp_id & (uint32_t)(lv.num_replicas - 1)) : 0u;
+    return r == 0 ? lv.feature_grads : lv.grad_replicas + (size_t)(r - 1) * (size_t)lv.rows * F;
+}
+
+// nodes_lookup_tables[level].get(morton, [-1]*8)  (model/feature_octree.py:205-209) as an open-addressing probe.
+// Returns the slot index or -1.  The first probe loads key speculatively together with the caller's id loads.
+__device__ __forceinline__ int probe_slot(const HashSlot* __restrict__ slots, uint32_t mask, unsigned long long key) {
+    uint32_t h = hash_key(key) & mask;
+#pragma unroll 1
+    for (uint32_t n = 0; n <= mask; ++n) {
+        const unsigned long long k = __ldg(&slots[h].key);
+        if (k == key) return (int)h;
+        if (k == kEmptyKey) return -1;
+        h = (h + 1) & mask;
+    }
+    return -1;
+}
+
+__device__ __noinline__ int probe_slot_from(const HashSlot* __restrict__ slots, uint32_t mask, unsigned long long key,
+                                            uint32_t start) {
+    uint32_t h = start & mask;
+#pragma unroll 1
+    for (uint32_t n = 0; n < mask; ++n) {
+        const unsigned long long k = __ldg(&slots[h].key);
+        if (k == key) return (int)h;
+        if (k == kEmptyKey) return -1;
+        h = (h + 1) & mask;
+    }
+    return -1;
+}
+
+
+// ------------------------------------------------------------------------------------------------------
+// host-side helpers shared by the entry points
+// ------------------------------------------------------------------------------------------------------
+
+constexpr int kMaxDevices = 64;
+
+inline bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
+
+// Every entry point launches on the device that OWNS its buffers, not on whatever device happens to be current:
+// the guard looks the device up from a representative device pointer and restores the previous device on exit.
+// Pinned-host / unregistered pointers leave the current device alone.
+struct DeviceGuard {
+    int prev = -1, dev = -1;
+    bool switched = false;
+    explicit DeviceGuard(const void* p) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; (void)cudaGetLastError(); }
+        dev = prev;
+        if (!p) return;
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return; }
+        if (a.type != cudaMemoryTypeDevice && a.type != cudaMemoryTypeManaged) return;
+        dev = a.device;
+        if (dev != prev && cudaSetDevice(dev) == cudaSuccess) switched = true;
+    }
+    ~DeviceGuard() { if (switched) (void)cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// device ordinal that owns `p`, or -1 for host / unknown pointers
+inline int device_of(const void* p) {
+    if (!p) return -1;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return -1; }
+    return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
+}
+
+inline int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+    return dev;
+}
+
+inline int sm_count() {
+    static int cached[kMaxDevices] = {0};
+    const int dev = current_device();
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+inline int check_octree(const shine_octree* o, bool need_grads) {
+    if (!o) return SHINE_ERR_INVALID_ARG;
+    if (o->num_levels < 1 || o->num_levels > SHINE_MAX_LEVELS) return SHINE_ERR_INVALID_ARG;
+    if (o->feature_dim < 4 || (o->feature_dim & 3)) return SHINE_ERR_UNSUPPORTED;
+    for (int i = 0; i < o->num_levels; ++i) {
+        const shine_level& lv = o->lv[i];
+        if (!lv.hash_slots || !lv.features || !is_pow2(lv.hash_capacity) || lv.rows < 1) return SHINE_ERR_INVALID_ARG;
+        if (lv.level < 1 || lv.level > 16) return SHINE_ERR_INVALID_ARG;
+        if (need_grads && !lv.feature_grads) return SHINE_ERR_INVALID_ARG;
+        if (lv.num_replicas > 1 && (!is_pow2((uint32_t)lv.num_replicas) || lv.num_replicas > 64 || !lv.grad_replicas))
+            return SHINE_ERR_INVALID_ARG;
+    }
+    return SHINE_OK;
+}
+
+// the batch must live on the same device as the tables (pinned host memory is allowed: the kernels can read it
+// through the unified address space)
+inline int check_same_device(const shine_octree* o, const void* batch_ptr) {
+    const int d = device_of(batch_ptr);
+    return (d >= 0 && d != device_of(o->lv[0].features)) ? SHINE_ERR_INVALID_ARG : SHINE_OK;
+}
+
+}  // namespace

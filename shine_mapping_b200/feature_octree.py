@@ -202,6 +202,7 @@ class FeatureOctree(nn.Module):
             raise ValueError(f'tree_level_feat > {_abi.MAX_LEVELS} is not supported by the sm_100a kernels')
         self._levels = [_LevelState(self.device) for _ in range(self.max_level + 1)]
         self._dict_cache = None
+        self._desc_cache = {}
         self._grad_scratch = {}   # k -> zero-invariant replica scratch (gradient privatisation)
         # coarse -> fine; the last row of each table is the trash-bin (reference :61-63)
         self.hier_features = nn.ParameterList([])
@@ -248,7 +249,7 @@ class FeatureOctree(nn.Module):
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_dict_cache"] = None
-        state["_desc_cache"] = None
+        state["_desc_cache"] = {}
         state["_grad_scratch"] = {}
         state["_last_coord"] = None
         state["_hier_idx"] = []
@@ -272,7 +273,7 @@ class FeatureOctree(nn.Module):
             st.hash, st.hash_capacity, st.hash_count = None, 0, 0
         self.importance_weight = [fn(t) for t in self.importance_weight]
         self.features_last_frame = [fn(t) for t in self.features_last_frame]
-        self._grad_scratch, self._desc_cache, self._last_coord, self._hier_idx = {}, None, None, []
+        self._grad_scratch, self._desc_cache, self._last_coord, self._hier_idx = {}, {}, None, []
         if len(self.hier_features):
             self.device = self.hier_features[0].device
         return self
@@ -280,10 +281,11 @@ class FeatureOctree(nn.Module):
     # ---- reference API -------------------------------------------------------------------------------------
 
     def set_zero(self):
-        """Re-zero the trash-bin rows (reference :78-81)."""
-        with torch.no_grad():
-            for p in self.hier_features:
-                p[-1].zero_()
+        """Re-zero the trash-bin rows (reference :78-81).  Written through `.data`: the reference does this with an
+        untracked copy too (:80-81), so a second query before the first result is back-propagated must not trip
+        autograd's saved-tensor version check (shine_batch.py:155-160 queries `coord_near` that way)."""
+        for p in self.hier_features:
+            p.data[-1].zero_()
 
     def forward(self, x):
         return self.query_feature(x)
@@ -370,6 +372,7 @@ class FeatureOctree(nn.Module):
             st.node_ids = torch.cat((st.node_ids, ids))
             st.node_keys_sorted = torch.sort(torch.cat((st.node_keys_sorted, new_m))).values
         self._dict_cache = None
+        self._desc_cache = {}
         self._hier_idx = []
         self._last_coord = None
 
@@ -397,16 +400,26 @@ class FeatureOctree(nn.Module):
                 continue
             _abi.require_cuda(st.node_keys, "FeatureOctree device tables")
             start = st.hash_count
-            if st.hash is None or self._HASH_SLOTS_PER_NODE * n > 2 * st.hash_capacity:
-                st.hash_capacity = _next_pow2(self._HASH_SLOTS_PER_NODE * max(n, 1))
+            spn = max(1, int(self._HASH_SLOTS_PER_NODE))
+            # grow when the load factor would pass 2/spn, and always keep at least one empty slot (a full table
+            # would turn every miss into a walk over the whole table)
+            if st.hash is None or spn * n > 2 * st.hash_capacity or n + 1 > st.hash_capacity:
+                st.hash_capacity = _next_pow2(max(spn * max(n, 1), n + 1))
                 st.hash = torch.full((st.hash_capacity * _abi.HASH_SLOT_BYTES,), 0xFF, dtype=torch.uint8,
                                      device=st.node_keys.device)
                 start = 0
             keys = st.node_keys[start:].contiguous()
             ids = st.node_ids[start:].contiguous()
+            overflow = torch.zeros(1, dtype=torch.int32, device=keys.device)
             _abi.check(lib.shine_hash_insert(_abi.ptr(st.hash), st.hash_capacity, _abi.ptr(keys), _abi.ptr(ids),
-                                             n - start, start, _abi.stream_ptr(keys.device)), "shine_hash_insert")
+                                             n - start, start, _abi.ptr(overflow), _abi.stream_ptr(keys.device)),
+                       "shine_hash_insert")
+            dropped = int(overflow.item())     # once per update(), never inside the training loop
+            if dropped:
+                raise _abi.ShineB200Error(f"device node table of level {i} overflowed: {dropped} of {n - start} keys "
+                                          f"were not stored (capacity {st.hash_capacity})")
             st.hash_count = n
+            self._desc_cache = {}
 
     # open addressing, linear probing: capacity = pow2 >= SLOTS_PER_NODE * nodes at (re)build time, rebuilt when the
     # load factor would exceed 2/SLOTS_PER_NODE.  4 -> load factor <= 0.25..0.5: ~1.2 probes per hit, ~1.4 per miss
@@ -444,11 +457,17 @@ class FeatureOctree(nn.Module):
         self._ensure_hash()
         tables = list(self.hier_features) if tables is None else list(tables)
         # building the ctypes struct costs ~20 us of Python: reuse it while the same buffers are passed
-        sig = (tuple(t.data_ptr() for t in tables), tuple(g.data_ptr() if g is not None else 0 for g in grads)
-               if grads is not None else None, n_points, tuple(st.hash.data_ptr() for st in self._levels if st.hash is not None))
-        cached = getattr(self, "_desc_cache", None)
-        if cached is not None and cached[0] == sig:
-            return cached[1]
+        # (the signature carries shapes and capacities too: the caching allocator may hand a re-grown table the
+        # address of an old one)
+        sig = (tuple((t.data_ptr(), t.shape[0]) for t in tables),
+               tuple(g.data_ptr() if g is not None else 0 for g in grads) if grads is not None else None, n_points,
+               tuple((st.hash.data_ptr(), st.hash_capacity) for st in self._levels if st.hash is not None))
+        cache = getattr(self, "_desc_cache", None)
+        if not isinstance(cache, dict):
+            cache = self._desc_cache = {}
+        hit = cache.get(sig)
+        if hit is not None:
+            return hit
         d = _abi.ShineOctree()
         d.num_levels = self.featured_level_num
         d.feature_dim = self.feature_dim
@@ -472,7 +491,9 @@ class FeatureOctree(nn.Module):
                 r, buf = self._replicas_for(k, t.shape[0], n_points, t.device)
                 if r > 1:
                     lv.num_replicas, lv.grad_replicas = r, buf.data_ptr()
-        self._desc_cache = (sig, d)
+        if len(cache) >= 8:      # forward / train / indices descriptors alternate inside one loop iteration
+            cache.clear()
+        cache[sig] = d
         return d
 
     def _prep_coord(self, coord):

@@ -45,7 +45,7 @@ def cal_feature_importance(trainer: SdfTrainer, octree: FeatureOctree, coord_poo
         c = coord_pool[head:min(head + interval, n):down_rate].contiguous()
         l = label_pool[head:min(head + interval, n):down_rate].contiguous()
         trainer.zero_grad()
-        trainer.forward_backward(c, l)
+        trainer.forward_backward(c, l, weighted=False)     # utils/incre_learning.py:33: weight=None
         for k in range(len(octree.importance_weight)):
             octree.importance_weight[k] += trainer.table_grads[k].abs()
             octree.importance_weight[k][-1] *= 0

@@ -95,13 +95,18 @@ class SdfTrainer:
 
     # ---- the hot path --------------------------------------------------------------------------------------
 
-    def forward_backward(self, coord, sdf_label, weight=None, n_norm=None, pred_out=None, accumulate_loss=False):
+    def forward_backward(self, coord, sdf_label, weight=None, n_norm=None, pred_out=None, accumulate_loss=False,
+                         weighted=None):
         """One fused launch: loss value (device scalar, accumulated into self.loss which is zeroed here) and
-        gradients accumulated into the flat buffer.  Caller zeroes grads (zero_grad / fused in optimizer_step)."""
+        gradients accumulated into the flat buffer.  Caller zeroes grads (zero_grad / fused in optimizer_step).
+        weighted: None = config.loss_weight_on (the loop, shine_batch.py:174); False = unweighted BCE whatever the
+        config says (what cal_feature_importance uses, utils/incre_learning.py:33)."""
         self._sync()
         cfg = self.config
         n = coord.shape[0]
-        weighted = bool(cfg.loss_weight_on)
+        weighted = bool(cfg.loss_weight_on) if weighted is None else bool(weighted)
+        if weighted and weight is None:
+            raise ValueError("loss_weight_on needs the per-sample weight tensor")
         flags = (_abi.FLAG_REDUCTION_SUM if cfg.loss_reduction == "sum" else 0) | \
                 (_abi.FLAG_WEIGHTED if weighted else 0) | (_abi.FLAG_TF32X1 if self.tf32x1 else 0)
         scale = 1.0 if cfg.loss_reduction == "sum" else 1.0 / float(n_norm if n_norm else n)
@@ -132,7 +137,9 @@ class SdfTrainer:
         device_step the step number / bias corrections live on the device (CUDA-graph replayable)."""
         cfg = self.config
         tables, dec = self._params()
-        self.step_count += 1
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:             # a captured call executes nothing: whoever replays the graph bumps the count
+            self.step_count += 1
         entries = []
         L = len(tables)
 
@@ -162,6 +169,11 @@ class SdfTrainer:
         _abi.check(_abi.lib().shine_adam_step(arr, len(entries), 0.9, 0.99, float(cfg.adam_eps), self.step_count,
                                               1 if zero_grad else 0, _abi.stream_ptr(tables[0].device)),
                    "shine_adam_step")
+
+    def _sync_adam_state(self):
+        """The host step_count is the single source of truth: write it to the device-side Adam state (the bump kernel
+        recomputes the bias corrections from the step number on every call)."""
+        self.adam_state[0] = max(int(self.step_count), 0)
 
     def train_step(self, coord, sdf_label, weight=None, n_norm=None):
         """shine_batch.py:123-210: fwd + loss + bwd (+ all-reduce when data parallel) + Adam."""
@@ -234,6 +246,8 @@ class SdfTrainer:
             with torch.cuda.graph(graph):
                 self._host_step_body(coord_h, label_h, weight_h, n, chunks, weighted, optimizer)
             self._host_graphs[key] = graph
+            if optimizer:             # bring the device counter back in line with the host one after the warm-up
+                self._sync_adam_state()
         graph.replay()
         if optimizer:
             self.step_count += 1      # the replayed Adam advanced the device-side step counter

@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert declared == set(_abi.SYMBOLS), declared ^ set(_abi.SYMBOLS)
     for name in declared:
         assert getattr(built_lib, name) is not None
-    assert built_lib.shine_abi_version() == 1
+    assert built_lib.shine_abi_version() == 2
     assert built_lib.shine_error_string(-2).decode().startswith("shine_b200: unsupported")
 
 
@@ -38,7 +38,7 @@ def test_abi_argument_checks_need_no_gpu(built_lib):
     assert built_lib.shine_query_fwd(C.byref(d), None, 4, None, None) == -1          # num_levels == 0
     d.num_levels, d.feature_dim = 1, 6
     assert built_lib.shine_query_fwd(C.byref(d), None, 4, None, None) == -2          # F not a multiple of 4
-    assert built_lib.shine_hash_insert(None, 16, None, None, 0, 0, None) == -1
+    assert built_lib.shine_hash_insert(None, 16, None, None, 0, 0, None, None) == -1
     assert built_lib.shine_points_to_morton(None, 0, 12, None, None) == 0            # empty is fine
 
 
