@@ -32,7 +32,9 @@ METRIC = "sdf_train_points_per_sec_fwd_bwd"
 UNIT = "points/s"
 L, F = 4, 8
 BYTES_PER_POINT = 24 + L * 40 + 3 * L * 8 * F * 4   # 3 256 B at L=4, F=8
+GATHER_BYTES_PER_POINT = L * 8 * F * 4               # the forward corner gather alone, 1 024 B
 HBM_FALLBACK_GBS = 6650.0
+PROFILE_JSON = os.path.join(ROOT, "profiles", "r02_kernel_counters.json")   # ncu-derived per-point counters
 
 
 def workload_config(device):
@@ -54,6 +56,14 @@ def build_workload(device, rank, world, n_azimuth):
     pool = synth.build_scene_map(cfg, octree, n_azimuth=n_azimuth, n_frames=1, seed=42 + rank, device=device,
                                  origin_x0=x0)
     return cfg, octree, decoder, pool
+
+
+def shared_config(cfg, n_azimuth, pool_len, n, world, rows):
+    """The `config` object of the JSON line — identical for our arm and the reference arm (same workload, same N)."""
+    return {"workload": cfg.name, "n_azimuth": n_azimuth, "pool_samples": pool_len, "points_per_step_per_gpu": n,
+            "global_points_per_step": n * world, "tree_level_feat": L, "feature_dim": F, "table_rows": rows,
+            "decoder": "geo_decoder_8dim arch 8-32-32-1, trainable", "loss": "sdf_bce mean",
+            "step": "grad zero + fwd + loss + bwd (table scatter-add + decoder grads); no optimizer"}
 
 
 def peaks():
@@ -166,14 +176,16 @@ def time_oracle(orc, o, dec, batches, sigma, steps, warmup):
 
 def run_reference(args):
     """The reference's own CPU algorithm for the path (oracle port: Python-dict Morton lookup + torch CPU
-    gather/MLP/BCE/autograd, all host threads), on a bounded sample of the C2 workload."""
+    gather/MLP/BCE/autograd, all host threads) on the SAME workload and the SAME points per step as our arm
+    (one whole-scan batch per step; `--ref-sample` bounds it only if the run would not end within minutes)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
     cfg, octree, decoder, pool = build_workload("cpu", 0, 1, args.n_azimuth)
     orc, o, dec = oracle_from_octree(octree, decoder)
-    sample = args.ref_sample
+    n = len(pool) if args.points <= 0 else args.points
+    sample = n if args.ref_sample <= 0 else min(n, args.ref_sample)
     gen = torch.Generator().manual_seed(7)
     batches = [pool.get_batch(sample, gen) for _ in range(2)]
     pick_threads(orc, o, dec, tuple(t[:20000] for t in batches[0]), cfg.sigma_sigmoid)
@@ -184,15 +196,183 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg.name, "n_azimuth": args.n_azimuth, "pool_samples": len(pool),
-                   "tree_level_feat": L, "feature_dim": F, "decoder": "geo_decoder_8dim arch 8-32-32-1",
-                   "loss": "sdf_bce mean", "points_per_step": sample},
+        "config": shared_config(cfg, args.n_azimuth, len(pool), n, max(args.gpus, 1),
+                                [int(p.shape[0]) for p in octree.hier_features]),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"{sample} randint-drawn samples of the {len(pool)}-sample C2 scan per step"},
+                         "sample": f"{sample} randint-drawn samples of the {len(pool)}-sample C2 scan per step "
+                                   f"(= the points_per_step_per_gpu of our arm)" if sample == n else
+                                   f"{sample} of the {n} points of a step (bounded by --ref-sample)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def kernel_counters():
+    """Per-point hardware counters of the step kernel taken from the committed ncu captures (profiles/): they turn the
+    live kernel time into a physical roofline.  r01 values as fallback."""
+    base = {"c2": {"lsu_wavefronts_per_point": 68.34, "dram_bytes_per_point": 36.87,
+                   "source": "profiles/r01_step_full_v5_details.csv (raw page of gpurun r01_step_full_v5.ncu-rep)"},
+            "hbm": {"dram_bytes_per_point": None, "source": None}}
+    try:
+        got = json.load(open(PROFILE_JSON))
+        for k in base:
+            base[k].update(got.get(k, {}))
+    except Exception:
+        pass
+    return base
+
+
+def time_steps(trainer, batches, steps, flush_buf, n_norm, dev, all_reduce=True):
+    """K steps with the L2 flushed before each; -> per-step (zero+kernel+reduce+allreduce), fused kernel alone, replica
+    reduce alone, in ms (means).  CUDA events on the launching stream."""
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(steps)]
+    for k in range(steps):
+        flush_buf.fill_(k & 0xFF)                     # > L2 (126 MB): evicts tables, inputs and gradients
+        b = batches[k % len(batches)]
+        ev[k][0].record()
+        trainer.zero_grad()
+        ev[k][1].record()
+        trainer.forward_backward(b[0], b[1], None, n_norm=n_norm, mid_event=ev[k][2])
+        ev[k][3].record()
+        if all_reduce:
+            trainer.all_reduce_grads()
+        ev[k][4].record()
+    torch.cuda.synchronize(dev)
+    mean = statistics.mean
+    return (mean(e[0].elapsed_time(e[4]) for e in ev), mean(e[1].elapsed_time(e[2]) for e in ev),
+            mean(e[2].elapsed_time(e[3]) for e in ev))
+
+
+def parity_block(orc, o, dec, trainer, octree, decoder, batch, sample, sigma):
+    """CUDA step vs the oracle on the first `sample` points of a bench batch (the oracle results of the cpu_baseline
+    leg are kept instead of being thrown away)."""
+    import numpy as np
+    c, l = batch[0][:sample].contiguous(), batch[1][:sample].contiguous()
+    res = orc.train_step(o, dec, c.cpu(), l.cpu(), None, sigma, False, "mean")
+    trainer.zero_grad()
+    pred = torch.empty(sample, device=c.device)
+    loss = float(trainer.forward_backward(c, l, None, pred_out=pred))
+    idx = octree.get_indices(c)
+    idx_exact = all(bool(torch.equal(a.cpu(), b)) for a, b in zip(idx, o.hierarchical_indices))
+
+    def rel(a, b):
+        b = b.double()
+        return float((a.detach().cpu().double() - b).abs().max() / b.abs().max().clamp_min(1e-30))
+    names = dict(decoder.named_parameters())
+    tg = max(rel(g[:-1], w[:-1]) for g, w in zip(trainer.table_grads, res["table_grads"]))
+    dg = max(rel(names[k].grad, w) for k, w in res["dec_grads"].items())
+    trainer.zero_grad()
+    return {"n_points": sample, "idx_exact": idx_exact,
+            "loss_rel": abs(loss - float(res["loss"])) / abs(float(res["loss"])),
+            "pred_max_abs": float((pred.cpu() - res["pred"]).abs().max()),
+            "table_grad_rel": tg, "dec_grad_rel": dg,
+            "tolerance": {"idx": "exact", "loss_rel": 2e-5, "grad_rel": 2e-4},
+            "ok": bool(idx_exact and tg <= 2e-4 and dg <= 2e-4)}
+
+
+def hbm_leg(args, dev, peak):
+    """The same step kernel on a map far larger than L2 (C3-like: many frames, leaf 0.05 m): the regime where the
+    HBM roofline is physical.  Algorithmic bytes / measured kernel time against the measured copy bandwidth, plus the
+    gather-only figure (1 024 B/pt over the forward kernel) for north_star's 60 % clause."""
+    import ctypes as C
+    from shine_mapping_b200 import Decoder, FeatureOctree, SdfTrainer, _abi, synth
+    cfg = workload_config(str(dev))
+    cfg.name = "c3_like_large_map"
+    cfg.leaf_vox_size = 0.05
+    cfg.calculate_world_scale()
+    torch.manual_seed(42)
+    octree, decoder = FeatureOctree(cfg), Decoder(cfg)
+    t0 = time.time()
+    pool = synth.build_scene_map(cfg, octree, n_azimuth=args.n_azimuth, n_frames=args.hbm_frames, frame_step_m=3.0,
+                                 seed=42, device=str(dev))
+    build_s = time.time() - t0
+    rows = [int(p.shape[0]) for p in octree.hier_features]
+    table_mb = sum(rows) * F * 4 / 1e6
+    n = args.hbm_points
+    trainer = SdfTrainer(cfg, octree, decoder)
+    gen = torch.Generator(device=dev).manual_seed(3)
+    batches = [pool.get_batch(n, gen) for _ in range(4)]
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for i in range(3):
+        trainer.zero_grad(); trainer.forward_backward(batches[i][0], batches[i][1], None)
+    torch.cuda.synchronize(dev)
+    steps = max(5, min(args.steps, 20))
+    step_ms, kern_ms, red_ms = time_steps(trainer, batches, steps, flush_buf, n, dev, all_reduce=False)
+    # forward kernel (hash walk + gather + blend + MLP + loss): the gather figure
+    od = octree._descriptor(None, None)
+    dd = decoder.c_descriptor(None)
+    pred = torch.empty(n, device=dev); loss = torch.zeros((), device=dev)
+    lib, st = _abi.lib(), _abi.stream_ptr(dev)
+
+    def fwd(b):
+        _abi.check(lib.shine_sdf_bce_fwd(C.byref(od), C.byref(dd), _abi.ptr(b[0]), _abi.ptr(b[1]), None, n,
+                                         float(cfg.sigma_sigmoid), 1.0 / n, _abi.ptr(pred), _abi.ptr(loss), 0, st),
+                   "shine_sdf_bce_fwd")
+    feat = torch.empty(n, F, device=dev)
+
+    def gather(b):
+        _abi.check(lib.shine_query_fwd(C.byref(od), _abi.ptr(b[0]), n, _abi.ptr(feat), st), "shine_query_fwd")
+    out = {}
+    for name, fn in (("fwd", fwd), ("gather", gather)):
+        for i in range(3):
+            fn(batches[i])
+        ts = []
+        for k in range(steps):
+            flush_buf.fill_(k & 0xFF)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(batches[k % 4]); e1.record(); torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1))
+        out[name] = statistics.mean(ts)
+    cnt = kernel_counters()["hbm"]
+    achieved = n * BYTES_PER_POINT / (kern_ms * 1e-3) / 1e9
+    g_fwd = n * GATHER_BYTES_PER_POINT / (out["fwd"] * 1e-3) / 1e9
+    g_only = n * GATHER_BYTES_PER_POINT / (out["gather"] * 1e-3) / 1e9
+    del flush_buf
+    return {
+        "bound": "hbm", "kernel": "sdf_fused_kernel<3,train,dec_grad,4>", "workload": cfg.name,
+        "frames": args.hbm_frames, "table_rows": rows, "table_mb": table_mb, "grad_mb": table_mb,
+        "points_per_step": n, "build_s": round(build_s, 1),
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "kernel_ms": kern_ms, "replica_reduce_ms": red_ms, "step_ms": step_ms,
+        "points_per_s": n / (step_ms * 1e-3),
+        "algorithmic_bytes_per_point": BYTES_PER_POINT,
+        "traffic": (cnt["dram_bytes_per_point"] * n) if cnt.get("dram_bytes_per_point") else None,
+        "traffic_source": cnt.get("source"),
+        "gather": {"bytes_per_point": GATHER_BYTES_PER_POINT,
+                   "forward_kernel_ms": out["fwd"], "forward_kernel_gbps": g_fwd, "forward_kernel_frac": g_fwd / peak,
+                   "gather_only_kernel_ms": out["gather"], "gather_only_gbps": g_only, "gather_only_frac": g_only / peak,
+                   "note": "north_star clause: >= 0.60 of the HBM roofline for the feature gather"},
+        "l2": "flushed between timed launches (256 MiB write, not timed); tables + gradients are > 2x the 126 MB L2",
+    }
+
+
+def small_batch_records(cfg, octree, decoder, pool, dev, sizes=(4096, 8192), iters=200):
+    """The reference's own batch sizes (config/*/*.yaml batch_size): one loop iteration {get_batch -> fused step ->
+    Adam(+zero grads)} replayed as a CUDA graph (batch_loop._GraphedIteration)."""
+    from shine_mapping_b200 import SdfTrainer
+    from shine_mapping_b200.batch_loop import _GraphedIteration
+    out = []
+    state = [p.detach().clone() for p in list(octree.parameters()) + list(decoder.parameters())]
+    for bs in sizes:
+        tr = SdfTrainer(cfg, octree, decoder)
+        tr.zero_grad()
+        it = _GraphedIteration(tr, pool, bs)
+        for _ in range(5):
+            it.run()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            it.run()
+        e1.record(); torch.cuda.synchronize(dev)
+        us = e0.elapsed_time(e1) * 1e3 / iters
+        out.append({"bs": bs, "us_per_iter": us, "iters_per_s": 1e6 / us, "points_per_s": bs * 1e6 / us,
+                    "iteration": "get_batch (randint gather) + fused fwd/loss/bwd + dense Adam with grad re-zero, CUDA graph"})
+    with torch.no_grad():      # the timing loop trained the model: put the weights back
+        for p, q in zip(list(octree.parameters()) + list(decoder.parameters()), state):
+            p.copy_(q)
+    return out
 
 
 def run_ours(args):
@@ -205,13 +385,13 @@ def run_ours(args):
         raise SystemExit("bench.py (our arm) needs a CUDA device: the hot path has no CPU fallback")
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    sdist.pin_to_gpu_numa_node(local)          # host threads + pinned buffers on the GPU's own NUMA node
     cfg, octree, decoder, pool = build_workload(str(dev), rank, world, args.n_azimuth)
     n = len(pool) if args.points <= 0 else args.points
     trainer = SdfTrainer(cfg, octree, decoder, shard_mode="spatial")
     n_global = n * world
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     batches = [pool.get_batch(n, gen) for _ in range(4)]
-    host = [tuple(t.cpu().pin_memory() for t in b[:2]) for b in batches]
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step(b):
@@ -219,12 +399,12 @@ def run_ours(args):
         trainer.forward_backward(b[0], b[1], None, n_norm=n_global)
         trainer.all_reduce_grads()
 
-    for i in range(max(args.warmup, 3)):
+    warm = max(args.warmup, 3)
+    for i in range(warm):
         step(batches[i % 4])
     torch.cuda.synchronize(dev)
 
     # ---- `value`: inputs resident in HBM, CUDA events on the launching stream, L2 flushed between steps ----
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.wait_first_sample()
@@ -233,24 +413,14 @@ def run_ours(args):
     t_clk0 = time.time()
     if args.cuda_profiler:
         torch.cuda.profiler.start()                   # ncu --profile-from-start off: only the timed steps
-    for k in range(args.steps):
-        flush_buf.fill_(k & 0xFF)                     # > L2 (126 MB): evicts tables, inputs and gradients
-        b = batches[k % 4]
-        ev[k][0].record()
-        trainer.zero_grad()
-        ev[k][1].record()
-        trainer.forward_backward(b[0], b[1], None, n_norm=n_global)
-        ev[k][2].record()
-        trainer.all_reduce_grads()
-        ev[k][3].record()
-    torch.cuda.synchronize(dev); sdist.barrier(dev)
+    step_ms, kern_ms, red_ms = time_steps(trainer, batches, args.steps, flush_buf, n_global, dev)
+    sdist.barrier(dev)
     if args.cuda_profiler:
         torch.cuda.profiler.stop()
     launches = _abi.LAUNCHES["count"] - launches0
-    step_ms = statistics.mean(e[0].elapsed_time(e[3]) for e in ev)
-    kern_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in ev)
     step_ms = sdist.max_over_ranks(step_ms, dev)
     kern_ms_max = sdist.max_over_ranks(kern_ms, dev)
+    red_ms_max = sdist.max_over_ranks(red_ms, dev)
     # nvidia-smi cannot sample faster than ~20 ms: keep the SAME steps running (not counted) so that the sampled
     # window under load is ~0.5 s.  The count is derived from the rank-agreed step time: every rank issues the same
     # number of collectives.
@@ -263,63 +433,98 @@ def run_ours(args):
     clocks = sampler.stop(t_clk0, time.time()) if sampler else None
     value = n_global / (step_ms * 1e-3)
 
-    # ---- `e2e`: host (pinned) buffers through SdfTrainer.step_from_host, wall clock incl. H2D + loss D2H -------
-    for i in range(max(4, args.warmup)):            # every pinned host batch once: its CUDA graph is captured untimed
-        trainer.step_from_host(*host[i % 4])
-    e2e_ts = []
+    # ---- `e2e`: pinned HOST buffers through the public host-step API; every step copies its inputs host->device
+    #      and reads its loss back.  Pipelined: step k+1's copy overlaps step k's kernels (submit/result); the inputs
+    #      rotate over host batches that together exceed L2.  The synchronous call is reported next to it. ----
+    n_host = max(4, min(16, (160 << 20) // max(1, n * 16) + 1))
+    host = []
+    for i in range(n_host):
+        b = pool.get_batch(n, gen)
+        host.append(tuple(t.cpu().pin_memory() for t in b[:2]))
+    for i in range(max(4, warm)):
+        trainer.submit_host_step(*host[i % n_host], n_norm=n_global).result()
+    sdist.barrier(dev); torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    pending, losses = None, []
+    for k in range(args.steps):
+        h = trainer.submit_host_step(*host[k % n_host], n_norm=n_global)
+        if pending is not None:
+            losses.append(pending.result())
+        pending = h
+    losses.append(pending.result())
+    torch.cuda.synchronize(dev)
+    e2e_sec = sdist.max_over_ranks((time.perf_counter() - t0) / args.steps, dev)
+    e2e_value = n_global / e2e_sec
+    for i in range(4):            # synchronous variant: every pinned host batch once -> its CUDA graph is captured untimed
+        trainer.step_from_host(*host[i])
+    sync_ts = []
     sdist.barrier(dev); torch.cuda.synchronize(dev)
     for k in range(args.steps):
         flush_buf.fill_(k & 0xFF)
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         trainer.step_from_host(*host[k % 4])          # ends with loss.item(): device -> host read
-        if world > 1:
-            trainer.all_reduce_grads(); torch.cuda.synchronize(dev)
-        e2e_ts.append(time.perf_counter() - t0)
-    e2e_sec = sdist.max_over_ranks(statistics.mean(e2e_ts), dev)
-    e2e_value = n_global / e2e_sec
+        sync_ts.append(time.perf_counter() - t0)
+    e2e_sync_sec = sdist.max_over_ranks(statistics.mean(sync_ts), dev)
 
     if rank != 0:
         return
+    del flush_buf
     peak, peak_src = peaks()
-    achieved = n * BYTES_PER_POINT / (kern_ms_max * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_step_kernel_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = float(json.load(open(tpath))["dram_bytes_per_point"]) * n
-        except Exception:
-            traffic = None
+    cnt = kernel_counters()
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    wf = cnt["c2"]["lsu_wavefronts_per_point"]
+    wf_rate = wf * n / (kern_ms_max * 1e-3) / 1e9                       # G wavefronts / s
+    wf_peak = n_sm * sm_mhz * 1e6 / 1e9                                  # 1 wavefront / clk / SM
+    alg = n * BYTES_PER_POINT / (kern_ms_max * 1e-3) / 1e9
+    rows = [int(p.shape[0]) for p in octree.hier_features]
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": cfg.name, "n_azimuth": args.n_azimuth, "points_per_step_per_gpu": n,
-                   "global_points_per_step": n_global, "tree_level_feat": L, "feature_dim": F,
-                   "table_rows": [int(p.shape[0]) for p in octree.hier_features],
-                   "decoder": "geo_decoder_8dim arch 8-32-32-1, trainable, 3xTF32 mma.sync",
-                   "loss": "sdf_bce mean", "parallelism": f"spatial-block x{world} + decoder-grad all-reduce",
-                   "l2": "flushed between timed steps (256 MiB write, not timed)",
-                   "step": "grad memset + fused fwd+loss+bwd kernel (+ all-reduce when N>1); no optimizer"},
-        "roofline": {"bound": "hbm", "kernel": "sdf_fused_kernel<3,train,dec_grad,4>",
-                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel_ms": kern_ms_max,
-                     "algorithmic_bytes_per_point": BYTES_PER_POINT},
+        "config": shared_config(cfg, args.n_azimuth, len(pool), n, world, rows),
+        "impl_notes": {"decoder_math": "3xTF32 mma.sync (fp32-grade)",
+                       "parallelism": f"spatial-block x{world} + decoder-grad all-reduce",
+                       "l2": "flushed between timed steps (256 MiB write, not timed)",
+                       "timed_step": "grad memset + fused fwd+loss+bwd kernel + replica fold (+ all-reduce when N>1)"},
+        # the C2 map (2.75 MB of features) lives in L2: the kernel's physical bound there is the L1TEX LSU data pipe
+        # (1 wavefront / clk / SM), not HBM.  wavefronts/point come from the committed ncu capture, time is live.
+        "roofline": {"bound": "l1tex_lsu", "kernel": "sdf_fused_kernel<3,train,dec_grad,4>",
+                     "achieved": wf_rate, "peak": wf_peak, "unit": "Gwavefront/s", "frac": wf_rate / wf_peak,
+                     "traffic": cnt["c2"]["dram_bytes_per_point"] * n, "kernel_ms": kern_ms_max,
+                     "replica_reduce_ms": red_ms_max,
+                     "lsu_wavefronts_per_point": wf, "counter_source": cnt["c2"]["source"],
+                     "peak_source": f"{n_sm} SMs x {sm_mhz:.0f} MHz x 1 wavefront/clk",
+                     "algorithmic_bytes_per_point": BYTES_PER_POINT, "algorithmic_gbps": alg,
+                     "algorithmic_over_hbm_peak": alg / peak,
+                     "note": "algorithmic bytes / time exceeds the HBM peak because >98 % of them are served by L2 "
+                             "(measured DRAM traffic in `traffic`); the HBM roofline proper is `roofline_hbm`"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": 4,
-                "ms_per_step": e2e_sec * 1e3},
+                "ms_per_step": e2e_sec * 1e3, "mode": "pipelined submit_host_step()/result(), depth 2",
+                "host_batches": n_host, "loss_last": losses[-1],
+                "sync": {"value": n_global / e2e_sync_sec, "ms_per_step": e2e_sync_sec * 1e3,
+                         "mode": "step_from_host(): copy, step and loss read-back strictly inside one call"}},
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    if world == 1 and not args.no_hbm_leg:
+        free_state = (trainer, batches, host)
+        del free_state
+        line["roofline_hbm"] = hbm_leg(args, dev, peak)
+        line["roofline_hbm"]["peak_source"] = peak_src
     if world == 1 and not args.no_cpu_baseline:
+        line["small_batch"] = small_batch_records(cfg, octree, decoder, pool, dev)
         torch.set_num_threads(os.cpu_count() or 1)
         orc, o, dec = oracle_from_octree(octree, decoder)
-        sample = args.ref_sample
+        sample = min(n, args.ref_sample if args.ref_sample > 0 else 100000)
         cb = [tuple(t[:sample].cpu() for t in b) for b in batches[:2]]
         pick_threads(orc, o, dec, tuple(t[:20000] for t in cb[0]), cfg.sigma_sigmoid)
         ts = time_oracle(orc, o, dec, cb, cfg.sigma_sigmoid, 3, 1)
         line["cpu_baseline"] = {"value": sample / statistics.mean(ts), "unit": UNIT, "cores": torch.get_num_threads(),
                                 "kind": "port", "sample": f"first {sample} points of the step's batch, 1 warm-up + 3 "
                                                            "timed oracle steps (Python-dict lookup + torch CPU autograd)"}
+        line["parity"] = parity_block(orc, o, dec, trainer, octree, decoder, batches[0], sample, cfg.sigma_sigmoid)
     print(json.dumps(line), flush=True)
 
 
@@ -331,7 +536,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-azimuth", type=int, default=2048, help="rays per ring of the synthetic scan (C2: 2048)")
     ap.add_argument("--points", type=int, default=0, help="points per step per GPU (default: the whole scan)")
-    ap.add_argument("--ref-sample", type=int, default=100000, help="points per oracle step (bounded CPU sample)")
+    ap.add_argument("--ref-sample", type=int, default=0,
+                    help="points per oracle step: reference arm default 0 = the whole step (same config as ours); "
+                         "cpu_baseline / parity legs of our arm default to 100000")
+    ap.add_argument("--hbm-frames", type=int, default=100, help="frames of the HBM-bound leg's map")
+    ap.add_argument("--hbm-points", type=int, default=1 << 20, help="points per step of the HBM-bound leg")
+    ap.add_argument("--no-hbm-leg", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-profiler", action="store_true", help="cudaProfilerStart/Stop around the timed steps")
     args = ap.parse_args()

@@ -22,8 +22,8 @@
 #include "shine_b200.h"
 
 // tuning switches (defaults = the best measured on B200; every alternative is in profiles/r01_summary.md)
-#ifndef SHINE_PREFETCH
-#define SHINE_PREFETCH 1      // software-pipeline the next tile's coord/label loads
+#ifndef SHINE_GATHER_GROUP
+#define SHINE_GATHER_GROUP 2  // levels whose first-probe sectors are in flight together (register pressure vs parallelism)
 #endif
 #ifndef SHINE_TRAIN_MINB
 #define SHINE_TRAIN_MINB 2    // min resident blocks/SM of the training kernel (register cap 65536/(256*MINB))
@@ -46,16 +46,20 @@ __global__ void hash_insert_kernel(HashSlot* __restrict__ slots, uint32_t mask, 
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long key = (unsigned long long)keys[i];
-    uint32_t h = hash_key(key) & mask;
+    const uint32_t h0 = hash_key(key) & mask;
     for (uint32_t it = 0; it <= mask; ++it) {
+        const uint32_t h = probe_pos(h0, it, mask);
         const unsigned long long prev = atomicCAS(&slots[h].key, kEmptyKey, key);
         if (prev == kEmptyKey || prev == key) {
             slots[h].node = node_base + (int32_t)i;
+            slots[h].key2 = key;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) slots[h].ids[(c >> 1) + 4 * (c & 1)] = corner_ids[i * 8 + c];
+            for (int c = 0; c < 4; ++c) {
+                slots[h].ids0[c] = corner_ids[i * 8 + 2 * c];
+                slots[h].ids1[c] = corner_ids[i * 8 + 2 * c + 1];
+            }
             return;
         }
-        h = (h + 1) & mask;
     }
     if (overflow) atomicAdd(overflow, 1);   // table full: the key was NOT stored — the caller must grow the table
 }
@@ -85,7 +89,7 @@ __global__ void get_indices_kernel(const __grid_constant__ shine_octree oct, con
 #pragma unroll
         for (int c = 0; c < 4; ++c) dst[c] = make_longlong2(-1, -1);
     } else {
-        const int4 a = ldg_i4(slots[s].ids), b = ldg_i4(slots[s].ids + 4);   // a: even corners, b: odd corners
+        const int4 a = ldg_i4(slots[s].ids0), b = ldg_i4(slots[s].ids1);   // a: even corners, b: odd corners
         dst[0] = make_longlong2(a.x, b.x); dst[1] = make_longlong2(a.y, b.y);
         dst[2] = make_longlong2(a.z, b.z); dst[3] = make_longlong2(a.w, b.w);
     }
@@ -111,7 +115,7 @@ __global__ void __launch_bounds__(256) query_fwd_kernel(const __grid_constant__ 
         const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
         const int s = probe_slot(slots, lv.hash_capacity - 1, morton_of(x, y, z, lv.level));
         if (s < 0) continue;
-        const int4 ia = ldg_i4(slots[s].ids), ib = ldg_i4(slots[s].ids + 4);
+        const int4 ia = ldg_i4(slots[s].ids0), ib = ldg_i4(slots[s].ids1);
         const int ids[8] = {ia.x, ib.x, ia.y, ib.y, ia.z, ib.z, ia.w, ib.w};   // un-permute (z-bit-major storage)
         float4 v[8];
 #pragma unroll
@@ -146,9 +150,12 @@ __global__ void __launch_bounds__(256) query_fwd8_kernel(const __grid_constant__
     for (int i = 0; i < oct.num_levels; ++i) {
         const shine_level& lv = oct.lv[i];
         const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
-        const int s = valid ? probe_slot(slots, lv.hash_capacity - 1, morton_of(x, y, z, lv.level)) : -1;
-        if (s < 0) continue;
-        const int4 id4 = ldg_i4(slots[s].ids + 4 * half);
+        if (!valid) continue;
+        const unsigned long long key = morton_of(x, y, z, lv.level);
+        const uint32_t mask = lv.hash_capacity - 1;
+        SlotSector sec = ldg_sector(slots, hash_key(key) & mask, half);
+        if (!resolve_sector(slots, mask, key, half, sec)) continue;
+        const int4 id4 = make_int4(sec.ids[0], sec.ids[1], sec.ids[2], sec.ids[3]);
         float r0[8], r1[8], r2[8], r3[8];
         ldg_row8(lv.features + (int64_t)id4.x * kF, r0);
         ldg_row8(lv.features + (int64_t)id4.y * kF, r1);
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(256) query_bwd_kernel(const __grid_constant__ 
         const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
         const int s = probe_slot(slots, lv.hash_capacity - 1, morton_of(x, y, z, lv.level));
         if (s < 0) continue;
-        const int4 ia = ldg_i4(slots[s].ids), ib = ldg_i4(slots[s].ids + 4);
+        const int4 ia = ldg_i4(slots[s].ids0), ib = ldg_i4(slots[s].ids1);
         const int ids[8] = {ia.x, ib.x, ia.y, ib.y, ia.z, ib.z, ia.w, ib.w};   // un-permute (z-bit-major storage)
         Blend b; b.init(x, y, z, lv.level, oct.poly_interp != 0);
         float* gb = grad_base(lv, (uint32_t)(gtid >> 5), F) + 4 * part;
@@ -266,7 +273,7 @@ __global__ void __launch_bounds__(256) query_tangent_kernel(const __grid_constan
         const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
         const int s = valid ? probe_slot(slots, lv.hash_capacity - 1, morton_of(x, y, z, lv.level)) : -1;
         if (s < 0) continue;
-        const int4 ia = ldg_i4(slots[s].ids), ib = ldg_i4(slots[s].ids + 4);
+        const int4 ia = ldg_i4(slots[s].ids0), ib = ldg_i4(slots[s].ids1);
         const int ids[8] = {ia.x, ib.x, ia.y, ib.y, ia.z, ib.z, ia.w, ib.w};   // un-permute (z-bit-major storage)
         BlendD b; b.init(x, y, z, lv.level, oct.poly_interp != 0);
 #pragma unroll
@@ -395,22 +402,24 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// register view: dW2[2][4][4] (cols 0..31), dW1[2][4] (32..39), db2[4][2] (40..47), db1[4][2] (48..55)
-#define SHINE_ACC_DECL float dW2[2][4][4], dW1[2][4], db2p[4][2], db1p[4][2]
+// register view: dW2[2][4][4] (cols 0..31), dW1[2][4] (32..39), db2[4][2] (40..47), db1[4][2] (48..55), dw3[4][2] (56..63)
+#define SHINE_ACC_DECL float dW2[2][4][4], dW1[2][4], db2p[4][2], db1p[4][2], dw3p[4][2]
 #define SHINE_ACC_LOAD(ta)                                                                             \
     do {                                                                                               \
         tmem_ld32((ta), &dW2[0][0][0]); tmem_ld8((ta) + 32, &dW1[0][0]); tmem_ld8((ta) + 40, &db2p[0][0]); \
-        tmem_ld8((ta) + 48, &db1p[0][0]); tmem_wait_ld();                                                \
+        tmem_ld8((ta) + 48, &db1p[0][0]); tmem_ld8((ta) + 56, &dw3p[0][0]); tmem_wait_ld();              \
     } while (0)
 #define SHINE_ACC_STORE(ta)                                                                            \
     do {                                                                                               \
         tmem_st32((ta), &dW2[0][0][0]); tmem_st8((ta) + 32, &dW1[0][0]); tmem_st8((ta) + 40, &db2p[0][0]); \
-        tmem_st8((ta) + 48, &db1p[0][0]); tmem_wait_st();                                                \
+        tmem_st8((ta) + 48, &db1p[0][0]); tmem_st8((ta) + 56, &dw3p[0][0]); tmem_wait_st();              \
     } while (0)
 
 // ------------------------------------------------------------------------------------------------------
 // the fused kernel: hash walk + gather + blend + MLP (+ BCE loss) (+ full backward with scatter-add)
 // ------------------------------------------------------------------------------------------------------
+
+constexpr int kGatherGroup = SHINE_GATHER_GROUP;
 
 struct StepParams {
     shine_octree oct;
@@ -442,7 +451,9 @@ struct SmemPlan {
     static constexpr int B3 = W3 + kH;                 // [1] (+3 pad)
     static constexpr int RED = B3 + 4;                 // block accumulator for decoder grads [1377 -> 1380]
     static constexpr int kDecGradFloats = kH * kF + kH + kH * kH + kH + kH + 1;   // 1377
-    static constexpr int STAGE = RED + 1380;           // per-warp staging: 2 x [16][kWS] + [16][8]
+    static constexpr int PRE = RED + 1380;             // per-warp input prefetch: [16][3] coord | [16] label | [16] weight
+    static constexpr int kPrePerWarp = 5 * kTile;
+    static constexpr int STAGE = PRE + 8 * kPrePerWarp;   // per-warp staging: 3 x [16][kWS] + [16][8]
     static constexpr int kStagePerWarp = 3 * kTile * kWS + kTile * kF;   // dh2 | h1 | dh1 | feat tiles
 };
 
@@ -505,7 +516,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
             dW1[a][0] = dW1[a][1] = dW1[a][2] = dW1[a][3] = 0.f;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { db2p[j][0] = db2p[j][1] = db1p[j][0] = db1p[j][1] = 0.f; }
+        for (int j = 0; j < 4; ++j) { db2p[j][0] = db2p[j][1] = db1p[j][0] = db1p[j][1] = dw3p[j][0] = dw3p[j][1] = 0.f; }
         SHINE_ACC_STORE(tacc);
     }
 
@@ -514,11 +525,8 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
     const float up = (TRAIN && P.d_loss) ? __ldg(P.d_loss) : 1.0f;
     const float gscale = P.loss_scale * up;
 
-    // decoder-gradient accumulators: dW2/dW1/db2/db1 are parked in TMEM (see DecGradAcc); only the 9 values of the
-    // output layer stay in registers
-    float dw3p[4][2], db3p = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { dw3p[j][0] = dw3p[j][1] = 0.f; }
+    // decoder-gradient accumulators: dW2/dW1/db2/db1/dw3 are parked in TMEM (SHINE_ACC_*); only db3 stays in a register
+    float db3p = 0.f;
     float loss_acc = 0.f;
 
     float* stage = smem + SmemPlan::STAGE + warp * SmemPlan::kStagePerWarp;   // only touched when DEC_GRAD
@@ -537,116 +545,105 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
     for (int i = 1; i < LMAX; ++i)
         if (i < L && P.oct.lv[i].level != P.oct.lv[0].level - i) consecutive = false;
 
-    // software pipeline, depth 1: the next tile's coordinates / label are in flight while this tile computes
-    float nx = 0.f, ny = 0.f, nz = 0.f, nlab = 0.f, nwgt = 1.f;
-    bool nvalid = false;
+    // software pipeline, depth 1: the next tile's coordinates / label / weight travel global -> shared memory with
+    // cp.async (no registers pinned, nothing to spill) while this tile computes
+    float* pre = smem + SmemPlan::PRE + warp * SmemPlan::kPrePerWarp;
+    const uint32_t pre_s = (uint32_t)__cvta_generic_to_shared(pre);
     auto prefetch_inputs = [&](int tl) {
-        const int64_t p = (int64_t)tl * kTile + g + 8 * odd;
-        nvalid = tl < P.num_tiles && p < P.n;
-        if (nvalid) {
-            nx = __ldg(P.coord + 3 * p); ny = __ldg(P.coord + 3 * p + 1); nz = __ldg(P.coord + 3 * p + 2);
-            if (P.label) nlab = __ldg(P.label + p);
-            if (P.weighted) nwgt = fabsf(__ldg(P.weight + p));   // shine_batch.py:172 abs()
+        if (tl < P.num_tiles) {
+            const int64_t base = (int64_t)tl * kTile;
+            const int64_t left = P.n - base;                      // > 0
+            const int npts = left < kTile ? (int)left : kTile;
+            // words 0..47: coord, 48..63: label, 64..79: weight
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int wd = lane + 32 * r;
+                const float* src = nullptr;
+                if (wd < 48) { if (wd < 3 * npts) src = P.coord + 3 * base + wd; }
+                else if (wd < 64) { if (P.label && wd - 48 < npts) src = P.label + base + (wd - 48); }
+                else if (wd < 80) { if (P.weighted && wd - 64 < npts) src = P.weight + base + (wd - 64); }
+                if (src) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(pre_s + 4u * (uint32_t)wd), "l"(src) : "memory");
+            }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
     prefetch_inputs(warp_global);
 
     for (int tile = warp_global; tile < P.num_tiles; tile += warp_stride) {
         const int64_t base = (int64_t)tile * kTile;
         const int64_t myp = base + g + 8 * odd;
-#if !SHINE_PREFETCH
-        prefetch_inputs(tile);
-#endif
-        const bool valid = nvalid;
-        const float x = nx, y = ny, z = nz, lab = nlab, wgt = nwgt;
-#if SHINE_PREFETCH
-        prefetch_inputs(tile + warp_stride);
-#endif
-
-        // ---- hash walk (model/feature_octree.py:199-218): all levels probed in parallel, the 8 corner ids are
-        //      fetched speculatively with the key (same 64-byte slot) so a first-probe hit costs ONE latency ----
-        // ---- hash walk (model/feature_octree.py:199-218).  The two lanes of a point split the LEVELS: lane `half`
-        //      probes levels half, half+2, ... (first-probe keys of all its levels in flight together), then the
-        //      pair exchanges slot indices.  Serial dependent probes per lane: 1 instead of L. ----
-        int slot[LMAX];
-        {
-            constexpr int LH = LMAX / 2;
-            const unsigned long long key0 = valid ? morton_of(x, y, z, P.oct.lv[0].level) : 0ull;
-            unsigned long long kq[LH], kf[LH];
-            int mine[LH];
-#pragma unroll
-            for (int j = 0; j < LH; ++j) {
-                const int i = 2 * j + half;
-                mine[j] = -1;
-                if (i < L && valid) {
-                    const shine_level& lv = P.oct.lv[i];
-                    const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
-                    kq[j] = consecutive ? (key0 >> (3 * i)) : morton_of(x, y, z, lv.level);
-                    mine[j] = (int)(hash_key(kq[j]) & (lv.hash_capacity - 1));
-                    kf[j] = __ldg(&slots[mine[j]].key);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < LH; ++j) {
-                const int i = 2 * j + half;
-                if (i < L && valid && kf[j] != kq[j]) {
-                    if (kf[j] == kEmptyKey) {
-                        mine[j] = -1;
-                    } else {   // first-probe collision (rare at load factor <= 0.5): walk on
-                        const shine_level& lv = P.oct.lv[i];
-                        mine[j] = probe_slot_from(reinterpret_cast<const HashSlot*>(lv.hash_slots),
-                                                  lv.hash_capacity - 1, kq[j], (uint32_t)mine[j] + 1);
-                    }
-                }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < LH; ++j) {
-                const int other = __shfl_xor_sync(kFull, mine[j], 2);
-                slot[2 * j] = half ? other : mine[j];
-                slot[2 * j + 1] = half ? mine[j] : other;
-            }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        const bool valid = myp < P.n;
+        float x = 0.f, y = 0.f, z = 0.f, lab = 0.f, wgt = 1.f;
+        if (valid) {
+            const int lp = g + 8 * odd;
+            x = pre[3 * lp]; y = pre[3 * lp + 1]; z = pre[3 * lp + 2];
+            if (P.label) lab = pre[48 + lp];
+            if (P.weighted) wgt = fabsf(pre[64 + lp]);   // shine_batch.py:172 abs()
         }
+        __syncwarp();
+        prefetch_inputs(tile + warp_stride);
 
-        // ---- 8-corner gather + blend, summed over levels (model/feature_octree.py:222-234).  The pair splits the
-        //      CORNERS: lane `half` fetches the corners with z bit == half as whole 32-byte rows (one LDG.256 each) and
-        //      blends all 8 channels; the two partial sums are then exchanged so that each lane ends with the 4
-        //      channels of its row-half. ----
+        // ---- hash walk + 8-corner gather + blend, summed over levels (model/feature_octree.py:199-234).
+        //      The two lanes of a point split the CORNERS by z bit: lane `half` reads sector `half` of the first-probe
+        //      slot of EVERY level with one 256-bit load (key + its 4 corner rows; all levels in flight together), then
+        //      fetches those rows whole (one LDG.256 each; the pair's two loads of one instruction hit z-neighbours =
+        //      consecutive table rows, usually one 128-byte line) and blends all 8 channels.  The partial sums are
+        //      exchanged so that each lane ends with the 4 channels of its row-half. ----
         float feat[4];
-        float pk[kPark];   // [3i..3i+2] = tx,ty,tz of level i; [3*LMAX + i] = slot index (parked in TMEM over the MLP)
-        float idp[kIdPark];   // [4i..4i+3] = rows of this lane's corners (z bit == half) of level i
+        float pk[kPark];      // [3i..3i+2] = tx,ty,tz of level i (parked in TMEM over the MLP phase)
+        float idp[kIdPark];   // [4i..4i+3] = rows of this lane's corners (z bit == half) of level i, -1 on a miss
+        uint32_t hitmask = 0;
         {
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int i = 0; i < kPark; ++i) pk[i] = 0.f;
+            const unsigned long long key0 = valid ? morton_of(x, y, z, P.oct.lv[0].level) : 0ull;
 #pragma unroll
-            for (int i = 0; i < kIdPark; ++i) idp[i] = 0.f;
+            for (int g0 = 0; g0 < LMAX; g0 += kGatherGroup) {
+                SlotSector sec[kGatherGroup];
 #pragma unroll
-            for (int i = 0; i < LMAX; ++i) {
-                if (i < L && slot[i] >= 0) {
-                    const shine_level& lv = P.oct.lv[i];
-                    const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
-                    // lane `half` takes the corners whose z bit is `half` (c = 2k + half): in every load instruction the
-                    // two lanes of a pair then fetch z-neighbours, whose rows are consecutive in the table (lexicographic
-                    // numbering) and usually share a 128-byte line -> one L1TEX wavefront instead of two
-                    const int4 id4 = ldg_i4(slots[slot[i]].ids + 4 * half);
-                    idp[4 * i] = __int_as_float(id4.x); idp[4 * i + 1] = __int_as_float(id4.y);
-                    idp[4 * i + 2] = __int_as_float(id4.z); idp[4 * i + 3] = __int_as_float(id4.w);
-                    float r0[8], r1[8], r2[8], r3[8];
-                    ldg_row8(lv.features + (int64_t)id4.x * kF, r0);
-                    ldg_row8(lv.features + (int64_t)id4.y * kF, r1);
-                    ldg_row8(lv.features + (int64_t)id4.z * kF, r2);
-                    ldg_row8(lv.features + (int64_t)id4.w * kF, r3);
-                    Blend b; b.init(x, y, z, lv.level, poly);
-                    pk[3 * i] = b.tx; pk[3 * i + 1] = b.ty; pk[3 * i + 2] = b.tz;
-                    const float wz = half ? b.tz : b.uz;
-                    const float w0 = __fmul_rn(__fmul_rn(b.ux, b.uy), wz), w1 = __fmul_rn(__fmul_rn(b.ux, b.ty), wz);
-                    const float w2 = __fmul_rn(__fmul_rn(b.tx, b.uy), wz), w3 = __fmul_rn(__fmul_rn(b.tx, b.ty), wz);
+                for (int j = 0; j < kGatherGroup; ++j) {
+                    const int i = g0 + j;
+                    if (i < L && valid) {
+                        const shine_level& lv = P.oct.lv[i];
+                        const unsigned long long kq = consecutive ? (key0 >> (3 * i)) : morton_of(x, y, z, lv.level);
+                        sec[j] = ldg_sector(reinterpret_cast<const HashSlot*>(lv.hash_slots),
+                                            hash_key(kq) & (lv.hash_capacity - 1), half);
+                    }
+                }
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        float a = acc[q];
-                        a = fmaf(w0, r0[q], a); a = fmaf(w1, r1[q], a); a = fmaf(w2, r2[q], a); a = fmaf(w3, r3[q], a);
-                        acc[q] = a;
+                for (int j = 0; j < kGatherGroup; ++j) {
+                    const int i = g0 + j;
+                    bool hit = false;
+                    if (i < L && valid) {
+                        const shine_level& lv = P.oct.lv[i];
+                        const unsigned long long kq = consecutive ? (key0 >> (3 * i)) : morton_of(x, y, z, lv.level);
+                        hit = resolve_sector(reinterpret_cast<const HashSlot*>(lv.hash_slots), lv.hash_capacity - 1, kq, half,
+                                             sec[j]);
+                    }
+                    idp[4 * i] = __int_as_float(hit ? sec[j].ids[0] : -1); idp[4 * i + 1] = __int_as_float(hit ? sec[j].ids[1] : -1);
+                    idp[4 * i + 2] = __int_as_float(hit ? sec[j].ids[2] : -1); idp[4 * i + 3] = __int_as_float(hit ? sec[j].ids[3] : -1);
+                    if (hit) {
+                        const shine_level& lv = P.oct.lv[i];
+                        hitmask |= 1u << i;
+                        float r0[8], r1[8], r2[8], r3[8];
+                        ldg_row8(lv.features + (int64_t)sec[j].ids[0] * kF, r0);
+                        ldg_row8(lv.features + (int64_t)sec[j].ids[1] * kF, r1);
+                        ldg_row8(lv.features + (int64_t)sec[j].ids[2] * kF, r2);
+                        ldg_row8(lv.features + (int64_t)sec[j].ids[3] * kF, r3);
+                        Blend b; b.init(x, y, z, lv.level, poly);
+                        pk[3 * i] = b.tx; pk[3 * i + 1] = b.ty; pk[3 * i + 2] = b.tz;
+                        const float wz = half ? b.tz : b.uz;
+                        const float w0 = __fmul_rn(__fmul_rn(b.ux, b.uy), wz), w1 = __fmul_rn(__fmul_rn(b.ux, b.ty), wz);
+                        const float w2 = __fmul_rn(__fmul_rn(b.tx, b.uy), wz), w3 = __fmul_rn(__fmul_rn(b.tx, b.ty), wz);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float a = acc[q];
+                            a = fmaf(w0, r0[q], a); a = fmaf(w1, r1[q], a); a = fmaf(w2, r2[q], a); a = fmaf(w3, r3[q], a);
+                            acc[q] = a;
+                        }
                     }
                 }
             }
@@ -658,8 +655,6 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
             }
         }
         if (TRAIN) {
-#pragma unroll
-            for (int i = 0; i < LMAX; ++i) pk[3 * LMAX + i] = __int_as_float(slot[i]);
             if (kPark == 16) tmem_st16(tpark, pk); else tmem_st32(tpark, pk);
             if (kIdPark == 16) tmem_st16(tpark + kPark, idp); else tmem_st32(tpark + kPark, idp);
             tmem_wait_st();
@@ -667,7 +662,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         if (!TRAIN && P.mask) {
             bool present = false;
 #pragma unroll
-            for (int i = 0; i < LMAX; ++i) present = (i == P.mask_level) ? (slot[i] >= 0) : present;
+            for (int i = 0; i < LMAX; ++i) present = (i == P.mask_level) ? (((hitmask >> i) & 1u) != 0) : present;
             if (half == 0 && valid) P.mask[myp] = (uint8_t)present;
         }
 
@@ -759,13 +754,13 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         const float dpx = __shfl_xor_sync(kFull, dpo, 1);
         const float dp0 = odd ? dpx : dpo, dp8 = odd ? dpo : dpx;
         float dh2[4][4];
-        float db2t[4][2], db1t[4][2];   // this tile's bias-gradient partials, folded into TMEM in the wgrad section
+        float db2t[4][2], db1t[4][2], dw3t[4][2];   // this tile's partials, folded into the TMEM accumulators in the wgrad section
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             dh2[j][0] = h2[j][0] > 0.f ? dp0 * w3a[j] : 0.f; dh2[j][1] = h2[j][1] > 0.f ? dp0 * w3b[j] : 0.f;
             dh2[j][2] = h2[j][2] > 0.f ? dp8 * w3a[j] : 0.f; dh2[j][3] = h2[j][3] > 0.f ? dp8 * w3b[j] : 0.f;
             if (DEC_GRAD) {
-                dw3p[j][0] += dp0 * h2[j][0] + dp8 * h2[j][2]; dw3p[j][1] += dp0 * h2[j][1] + dp8 * h2[j][3];
+                dw3t[j][0] = dp0 * h2[j][0] + dp8 * h2[j][2];  dw3t[j][1] = dp0 * h2[j][1] + dp8 * h2[j][3];
                 db2t[j][0] = dh2[j][0] + dh2[j][2];            db2t[j][1] = dh2[j][1] + dh2[j][3];
                 *reinterpret_cast<float2*>(stA + g * kWS + 8 * j + 2 * t) = make_float2(dh2[j][0], dh2[j][1]);
                 *reinterpret_cast<float2*>(stA + (g + 8) * kWS + 8 * j + 2 * t) = make_float2(dh2[j][2], dh2[j][3]);
@@ -817,6 +812,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
             for (int j = 0; j < 4; ++j) {
                 db2p[j][0] += db2t[j][0]; db2p[j][1] += db2t[j][1];
                 db1p[j][0] += db1t[j][0]; db1p[j][1] += db1t[j][1];
+                dw3p[j][0] += dw3t[j][0]; dw3p[j][1] += dw3t[j][1];
             }
             __syncwarp();
             // dW2[n2][k1] += sum_rows dh2[row][n2] * h1[row][k1]
@@ -864,7 +860,6 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < LMAX; ++i) {
-            const int sl = __float_as_int(qk[3 * LMAX + i]);
             // the 8 corner rows: this lane kept the 4 with z bit == half, its partner (lane ^ 2) the other 4
             int ids[8];
 #pragma unroll
@@ -874,7 +869,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                 ids[2 * k] = half ? other : mine;
                 ids[2 * k + 1] = half ? mine : other;
             }
-            if (i < L && sl >= 0) {
+            if (i < L && ids[0] >= 0) {      // a miss parked -1 for all of its rows
                 const shine_level& lv = P.oct.lv[i];
                 Blend b;
                 b.tx = qk[3 * i]; b.ty = qk[3 * i + 1]; b.tz = qk[3 * i + 2];
@@ -1071,72 +1066,55 @@ __global__ void __launch_bounds__(128, 5) sdf_infer_tc_kernel(const __grid_const
             const bool valid = p < P.n;
             float x = 0.f, y = 0.f, z = 0.f;
             if (valid) { x = __ldg(P.coord + 3 * p); y = __ldg(P.coord + 3 * p + 1); z = __ldg(P.coord + 3 * p + 2); }
-            int slot[LMAX];
-            {
-                constexpr int LH = LMAX / 2;
-                const unsigned long long key0 = valid ? morton_of(x, y, z, P.oct.lv[0].level) : 0ull;
-                unsigned long long kq[LH], kf[LH];
-                int mine[LH];
+            uint32_t hitmask = 0;
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const unsigned long long key0 = valid ? morton_of(x, y, z, P.oct.lv[0].level) : 0ull;
 #pragma unroll
-                for (int j = 0; j < LH; ++j) {
-                    const int i = 2 * j + half;
-                    mine[j] = -1;
+            for (int g0 = 0; g0 < LMAX; g0 += kGatherGroup) {
+                SlotSector sec[kGatherGroup];
+#pragma unroll
+                for (int j = 0; j < kGatherGroup; ++j) {
+                    const int i = g0 + j;
                     if (i < L && valid) {
                         const shine_level& lv = P.oct.lv[i];
-                        kq[j] = consecutive ? (key0 >> (3 * i)) : morton_of(x, y, z, lv.level);
-                        mine[j] = (int)(hash_key(kq[j]) & (lv.hash_capacity - 1));
-                        kf[j] = __ldg(&reinterpret_cast<const HashSlot*>(lv.hash_slots)[mine[j]].key);
+                        const unsigned long long kq = consecutive ? (key0 >> (3 * i)) : morton_of(x, y, z, lv.level);
+                        sec[j] = ldg_sector(reinterpret_cast<const HashSlot*>(lv.hash_slots),
+                                            hash_key(kq) & (lv.hash_capacity - 1), half);
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < LH; ++j) {
-                    const int i = 2 * j + half;
-                    if (i < L && valid && kf[j] != kq[j]) {
-                        if (kf[j] == kEmptyKey) mine[j] = -1;
-                        else {
-                            const shine_level& lv = P.oct.lv[i];
-                            mine[j] = probe_slot_from(reinterpret_cast<const HashSlot*>(lv.hash_slots), lv.hash_capacity - 1,
-                                                      kq[j], (uint32_t)mine[j] + 1);
+                for (int j = 0; j < kGatherGroup; ++j) {
+                    const int i = g0 + j;
+                    if (i < L && valid) {
+                        const shine_level& lv = P.oct.lv[i];
+                        const unsigned long long kq = consecutive ? (key0 >> (3 * i)) : morton_of(x, y, z, lv.level);
+                        if (!resolve_sector(reinterpret_cast<const HashSlot*>(lv.hash_slots), lv.hash_capacity - 1, kq, half,
+                                            sec[j]))
+                            continue;
+                        hitmask |= 1u << i;
+                        float q0[8], q1[8], q2[8], q3[8];                            // corners with z bit == half
+                        ldg_row8(lv.features + (int64_t)sec[j].ids[0] * kF, q0);
+                        ldg_row8(lv.features + (int64_t)sec[j].ids[1] * kF, q1);
+                        ldg_row8(lv.features + (int64_t)sec[j].ids[2] * kF, q2);
+                        ldg_row8(lv.features + (int64_t)sec[j].ids[3] * kF, q3);
+                        Blend b; b.init(x, y, z, lv.level, poly);
+                        const float wz = half ? b.tz : b.uz;
+                        const float w0 = __fmul_rn(__fmul_rn(b.ux, b.uy), wz), w1 = __fmul_rn(__fmul_rn(b.ux, b.ty), wz);
+                        const float w2 = __fmul_rn(__fmul_rn(b.tx, b.uy), wz), w3 = __fmul_rn(__fmul_rn(b.tx, b.ty), wz);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float a = acc[q];
+                            a = fmaf(w0, q0[q], a); a = fmaf(w1, q1[q], a); a = fmaf(w2, q2[q], a); a = fmaf(w3, q3[q], a);
+                            acc[q] = a;
                         }
                     }
-                }
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < LH; ++j) {
-                    const int other = __shfl_xor_sync(kFull, mine[j], 1);
-                    slot[2 * j] = half ? other : mine[j];
-                    slot[2 * j + 1] = half ? mine[j] : other;
                 }
             }
             if (P.mask && valid && half == 0) {
                 bool present = false;
 #pragma unroll
-                for (int i = 0; i < LMAX; ++i) present = (i == P.mask_level) ? (slot[i] >= 0) : present;
+                for (int i = 0; i < LMAX; ++i) present = (i == P.mask_level) ? (((hitmask >> i) & 1u) != 0) : present;
                 P.mask[p] = (uint8_t)present;
-            }
-            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int i = 0; i < LMAX; ++i) {
-                if (i < L && slot[i] >= 0) {
-                    const shine_level& lv = P.oct.lv[i];
-                    const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
-                    const int4 id4 = ldg_i4(slots[slot[i]].ids + 4 * half);       // corners with z bit == half
-                    float q0[8], q1[8], q2[8], q3[8];
-                    ldg_row8(lv.features + (int64_t)id4.x * kF, q0);
-                    ldg_row8(lv.features + (int64_t)id4.y * kF, q1);
-                    ldg_row8(lv.features + (int64_t)id4.z * kF, q2);
-                    ldg_row8(lv.features + (int64_t)id4.w * kF, q3);
-                    Blend b; b.init(x, y, z, lv.level, poly);
-                    const float wz = half ? b.tz : b.uz;
-                    const float w0 = __fmul_rn(__fmul_rn(b.ux, b.uy), wz), w1 = __fmul_rn(__fmul_rn(b.ux, b.ty), wz);
-                    const float w2 = __fmul_rn(__fmul_rn(b.tx, b.uy), wz), w3 = __fmul_rn(__fmul_rn(b.tx, b.ty), wz);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        float a = acc[q];
-                        a = fmaf(w0, q0[q], a); a = fmaf(w1, q1[q], a); a = fmaf(w2, q2[q], a); a = fmaf(w3, q3[q], a);
-                        acc[q] = a;
-                    }
-                }
             }
             // each lane keeps the 4 channels of its half (= one 16-byte K-chunk of the point's row of the A tile)
             uint32_t h4[4], l4[4];

@@ -22,13 +22,25 @@ constexpr int kWS = 40;            // padded row stride (floats) of 32-wide smem
 constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
+// One node of `nodes_lookup_tables[level]` (model/feature_octree.py:162-166) = one 64-byte slot made of two
+// self-contained 32-byte sectors: sector z holds a copy of the key and the rows of the 4 corners whose z bit is z.
+// The two lanes that share a point each read ONE sector with ONE 256-bit load and get key + their 4 corner rows at
+// once: a first-probe hit costs a single memory round trip before the feature rows can be requested.
 struct __align__(64) HashSlot {
     unsigned long long key;   // Morton code of the voxel, kEmptyKey when free
     int32_t node;             // insertion ordinal (diagnostics)
-    int32_t pad[5];
-    int32_t ids[8];           // rows of the 8 corners, stored z-bit-major: [c0 c2 c4 c6 | c1 c3 c5 c7] (second sector)
+    int32_t pad0;
+    int32_t ids0[4];          // rows of corners c0 c2 c4 c6 (z bit 0)
+    unsigned long long key2;  // copy of key (written after the slot is claimed through `key`)
+    int32_t pad1[2];
+    int32_t ids1[4];          // rows of corners c1 c3 c5 c7 (z bit 1)
 };
 static_assert(sizeof(HashSlot) == SHINE_HASH_SLOT_BYTES, "slot must be 64 bytes");
+
+// the 4 corner rows with z bit == half of slot s
+__device__ __forceinline__ const int32_t* slot_ids(const HashSlot* slots, int s, int half) {
+    return reinterpret_cast<const int32_t*>(slots + s) + 8 * half + 4;
+}
 
 // 64-bit mix (two multiplies).  A cheaper 32-bit fmix32 of the folded key was measured and rejected: more first-probe
 // collisions (gather-only kernel 0.111 -> 0.137 ms).
@@ -107,33 +119,68 @@ __device__ __forceinline__ float* grad_base(const shine_level& lv, uint32_t warp
     return r == 0 ? lv.feature_grads : lv.grad_replicas + (size_t)(r - 1) * (size_t)lv.rows * F;
 }
 
+// Probe sequence of key k in a table of mask+1 slots: p0 = hash & mask, p1 = p0 ^ 1 (the buddy slot in the same
+// 128-byte line: a second probe that hits L1), then linearly from the next pair on.  Visits every slot once.
+__host__ __device__ __forceinline__ uint32_t probe_pos(uint32_t h0, uint32_t k, uint32_t mask) {
+    return k == 0 ? h0 : (k == 1 ? (h0 ^ 1u) : (((h0 & ~1u) + k) & mask));
+}
+
 // nodes_lookup_tables[level].get(morton, [-1]*8)  (model/feature_octree.py:205-209) as an open-addressing probe.
-// Returns the slot index or -1.  The first probe loads key speculatively together with the caller's id loads.
+// Returns the slot index or -1.
 __device__ __forceinline__ int probe_slot(const HashSlot* __restrict__ slots, uint32_t mask, unsigned long long key) {
-    uint32_t h = hash_key(key) & mask;
+    const uint32_t h0 = hash_key(key) & mask;
 #pragma unroll 1
     for (uint32_t n = 0; n <= mask; ++n) {
+        const uint32_t h = probe_pos(h0, n, mask);
         const unsigned long long k = __ldg(&slots[h].key);
         if (k == key) return (int)h;
         if (k == kEmptyKey) return -1;
-        h = (h + 1) & mask;
     }
     return -1;
 }
 
+// continuation of a walk whose probes 0 .. first-1 have already been looked at (and were neither the key nor empty)
 __device__ __noinline__ int probe_slot_from(const HashSlot* __restrict__ slots, uint32_t mask, unsigned long long key,
-                                            uint32_t start) {
-    uint32_t h = start & mask;
+                                            uint32_t h0, uint32_t first) {
 #pragma unroll 1
-    for (uint32_t n = 0; n < mask; ++n) {
+    for (uint32_t n = first; n <= mask; ++n) {
+        const uint32_t h = probe_pos(h0, n, mask);
         const unsigned long long k = __ldg(&slots[h].key);
         if (k == key) return (int)h;
         if (k == kEmptyKey) return -1;
-        h = (h + 1) & mask;
     }
     return -1;
 }
 
+// one 32-byte sector of a slot: {key (2 words), 2 words of padding / ordinal, 4 corner rows}
+struct SlotSector { unsigned long long key; int32_t ids[4]; };
+__device__ __forceinline__ SlotSector ldg_sector(const HashSlot* slots, uint32_t s, int half) {
+    uint32_t w[8];
+    const void* p = reinterpret_cast<const char*>(slots + s) + 32 * half;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                 : "l"(p));
+    SlotSector r;
+    r.key = ((unsigned long long)w[1] << 32) | w[0];
+    r.ids[0] = (int32_t)w[4]; r.ids[1] = (int32_t)w[5]; r.ids[2] = (int32_t)w[6]; r.ids[3] = (int32_t)w[7];
+    return r;
+}
+
+// Full lookup as the pair-split kernels do it: lane `half` of a point reads sector `half` of the first-probe slot; on
+// a first-probe collision it walks on and fetches its 4 rows separately.  hit == false: ids are -1.
+__device__ __forceinline__ bool resolve_sector(const HashSlot* slots, uint32_t mask, unsigned long long key, int half,
+                                               SlotSector& sec) {
+    if (sec.key == key) return true;
+    int s = -1;
+    if (sec.key != kEmptyKey) s = probe_slot_from(slots, mask, key, hash_key(key) & mask, 1u);
+    if (s >= 0) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(slot_ids(slots, s, half)));
+        sec.ids[0] = v.x; sec.ids[1] = v.y; sec.ids[2] = v.z; sec.ids[3] = v.w;
+        return true;
+    }
+    sec.ids[0] = sec.ids[1] = sec.ids[2] = sec.ids[3] = -1;
+    return false;
+}
 
 // ------------------------------------------------------------------------------------------------------
 // host-side helpers shared by the entry points

@@ -58,3 +58,57 @@ def barrier(device=None):
             dist.barrier(device_ids=[torch.device(device).index or 0])
         else:
             dist.barrier()
+
+
+def gpu_numa_node(local_rank: int) -> int | None:
+    """NUMA node of GPU `local_rank` (sysfs numa_node of its PCI device, via NVML's bus id); None when unknown."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = local_rank
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local_rank < len(ids) and ids[local_rank].isdigit():
+                index = int(ids[local_rank])
+        handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(handle).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:            # NVML prints an 8-digit PCI domain, sysfs uses 4
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except Exception:
+        return None
+
+
+def _parse_cpulist(text: str) -> set[int]:
+    cpus: set[int] = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def pin_to_gpu_numa_node(local_rank: int) -> dict:
+    """Bind this process (and what it allocates afterwards: pinned staging buffers are first-touched locally) to the
+    CPUs of the NUMA node its GPU hangs off.  Eight ranks feeding eight GPUs from one socket halve the host->device
+    rate of the far GPUs (r01: e2e efficiency 0.61 at N=8).  No-op when the topology cannot be read."""
+    node = gpu_numa_node(local_rank)
+    info = {"numa_node": node, "cpus": None}
+    if node is None or not hasattr(os, "sched_setaffinity"):
+        return info
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, cpus)
+        info["cpus"] = len(cpus)
+    except Exception:
+        pass
+    return info

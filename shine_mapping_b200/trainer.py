@@ -96,7 +96,7 @@ class SdfTrainer:
     # ---- the hot path --------------------------------------------------------------------------------------
 
     def forward_backward(self, coord, sdf_label, weight=None, n_norm=None, pred_out=None, accumulate_loss=False,
-                         weighted=None):
+                         weighted=None, mid_event=None):
         """One fused launch: loss value (device scalar, accumulated into self.loss which is zeroed here) and
         gradients accumulated into the flat buffer.  Caller zeroes grads (zero_grad / fused in optimizer_step).
         weighted: None = config.loss_weight_on (the loop, shine_batch.py:174); False = unweighted BCE whatever the
@@ -119,6 +119,8 @@ class SdfTrainer:
             C.byref(od), C.byref(dd), _abi.ptr(coord), _abi.ptr(sdf_label),
             _abi.ptr(weight) if weighted else None, n, float(self.sigma), scale, None,
             _abi.ptr(pred_out), _abi.ptr(self.loss), flags, _abi.stream_ptr(coord.device)), "shine_sdf_bce_step")
+        if mid_event is not None:          # lets a profiler time the fused kernel and the replica fold separately
+            mid_event.record()
         if self.use_replicas:
             self.octree._reduce_replicas(od, coord.device)
         return self.loss
@@ -209,6 +211,60 @@ class SdfTrainer:
         if optimizer:
             self.all_reduce_grads()
             self.optimizer_step(zero_grad=False, device_step=True)
+
+    # ---- pipelined host-buffer entry ------------------------------------------------------------------------
+
+    class HostStepHandle:
+        """Result of `submit_host_step`: `.result()` blocks until that step's loss is on the host."""
+
+        def __init__(self, event, loss_host):
+            self._event, self._loss_host = event, loss_host
+
+        def result(self) -> float:
+            self._event.synchronize()
+            return float(self._loss_host.item())
+
+    def submit_host_step(self, coord_h, label_h, weight_h=None, n_norm=None, optimizer: bool = False):
+        """Asynchronous variant of `step_from_host` for loops that do not need step k's loss before building step k+1
+        (the reference loop reads the loss only for logging, shine_batch.py:215-226).  Two device staging slots: the
+        host->device copy of this batch runs on a copy stream while the previous step's kernels run on the main stream;
+        the loss is copied to a pinned host scalar and an event tells when it is there.  Every step still copies its
+        own inputs and reads its own result; only the waiting is overlapped."""
+        dev = self.flat_grad.device
+        n = coord_h.shape[0]
+        weighted = bool(self.config.loss_weight_on) and weight_h is not None
+        self._sync()
+        pl = getattr(self, "_pipe", None)
+        if pl is None or pl["cap"] < n or pl["sig"] != self._sig:
+            pl = {"cap": n, "sig": self._sig, "k": 0, "copy": torch.cuda.Stream(device=dev),
+                  "slots": [{"coord": torch.empty(n, 3, device=dev), "label": torch.empty(n, device=dev),
+                             "weight": torch.empty(n, device=dev), "free": None,
+                             "loss_h": torch.zeros(1).pin_memory()} for _ in range(2)]}
+            self._pipe = pl
+        slot = pl["slots"][pl["k"] & 1]
+        pl["k"] += 1
+        main, copy = torch.cuda.current_stream(dev), pl["copy"]
+        if slot["free"] is not None:
+            copy.wait_event(slot["free"])            # the kernels that read this slot two steps ago are done
+        with torch.cuda.stream(copy):
+            slot["coord"][:n].copy_(coord_h, non_blocking=True)
+            slot["label"][:n].copy_(label_h, non_blocking=True)
+            if weighted:
+                slot["weight"][:n].copy_(weight_h, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(copy)
+        main.wait_event(copied)
+        self.zero_grad()
+        self.forward_backward(slot["coord"][:n], slot["label"][:n], slot["weight"][:n] if weighted else None,
+                              n_norm=n_norm or n)
+        slot["loss_h"].copy_(self.loss.view(1), non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(main)
+        slot["free"] = done
+        if optimizer:
+            self.all_reduce_grads()
+            self.optimizer_step(zero_grad=False)
+        return SdfTrainer.HostStepHandle(done, slot["loss_h"])
 
     def step_from_host(self, coord_h, label_h, weight_h=None, optimizer: bool = False, chunks: int = 0,
                        use_graph: bool = True) -> float:
