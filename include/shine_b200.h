@@ -165,6 +165,44 @@ int shine_adam_step(const shine_adam_tensor* tensors, int32_t count, float beta1
 int shine_adam_step_dev(const shine_adam_tensor* tensors, int32_t count, float beta1, float beta2, float eps,
                         void* state, int32_t zero_grad, void* stream);
 
+/* ---- continual-learning terms of the incremental loop (BASELINE config 4) ---------------------------------------
+ * The reference finds the rows a batch touched with `hierarchical_indices[i].flatten().unique()` (a sort per level
+ * per step, model/feature_octree.py:251) and then works on dense [rows, F] tensors.  Here the touched rows of a batch
+ * are a compact per-level list: one bit per row in `bitmap` (all zero between uses), first setter appends the row. */
+typedef struct shine_touched_level {
+    uint32_t* bitmap;         /* [(rows + 31) / 32] words, zero on entry                                       */
+    int32_t* rows;            /* [capacity] touched row ids, unordered, each row once                           */
+    int32_t* count;           /* device scalar, zero on entry                                                   */
+    int32_t capacity;         /* >= min(rows, 8 n)                                                              */
+    int32_t reserved;
+} shine_touched_level;
+typedef struct shine_touched { shine_touched_level lv[SHINE_MAX_LEVELS]; } shine_touched;   /* bottom-up like shine_octree */
+
+/* per-level row-aligned side tables of the incremental loop, bottom-up: features_last_frame / importance_weight
+ * (model/feature_octree.py:70-72) */
+typedef struct shine_row_tables {
+    const float* last[SHINE_MAX_LEVELS];        /* features_last_frame (regularisation)                       */
+    const float* importance[SHINE_MAX_LEVELS];  /* importance_weight, read  (regularisation)                  */
+    float* importance_rw[SHINE_MAX_LEVELS];     /* importance_weight, updated (importance pass)               */
+} shine_row_tables;
+
+/* Collect the rows touched by `coord` (hit voxels only: the reference's -1 row has zero importance,
+ * utils/incre_learning.py:40).  Replaces the unique() of model/feature_octree.py:251. */
+int shine_mark_touched(const shine_octree* oct, const float* coord, int64_t n, const shine_touched* touched,
+                       void* stream);
+
+/* FeatureOctree.cal_regularization (model/feature_octree.py:246-255) and its gradient, over the touched rows only:
+ *   *out_reg (+=)         sum_u Omega[u] * (f[u] - f_last[u])^2
+ *   feature_grads[u] +=   grad_scale * Omega[u] * (f[u] - f_last[u])        (grad_scale = 2 * lambda_forget)
+ * clear_marks != 0 also clears the bitmap bits of the processed rows (leave it 0 when another pass follows). */
+int shine_regularization_apply(const shine_octree* oct, const shine_touched* touched, const shine_row_tables* aux,
+                               float grad_scale, float* out_reg, int32_t clear_marks, void* stream);
+
+/* cal_feature_importance's accumulation (utils/incre_learning.py:36-40) over the touched rows only:
+ *   importance_rw[u] += |feature_grads[u]|;  zero_grads != 0: feature_grads[u] = 0 afterwards (:38). */
+int shine_importance_accumulate(const shine_octree* oct, const shine_touched* touched, const shine_row_tables* aux,
+                                int32_t zero_grads, int32_t clear_marks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

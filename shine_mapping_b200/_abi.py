@@ -47,6 +47,20 @@ class ShineAdamTensor(C.Structure):
                 ("numel", C.c_int64), ("lr", C.c_float), ("weight_decay", C.c_float)]
 
 
+class ShineTouchedLevel(C.Structure):
+    _fields_ = [("bitmap", C.c_void_p), ("rows", C.c_void_p), ("count", C.c_void_p), ("capacity", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class ShineTouched(C.Structure):
+    _fields_ = [("lv", ShineTouchedLevel * MAX_LEVELS)]
+
+
+class ShineRowTables(C.Structure):
+    _fields_ = [("last", C.c_void_p * MAX_LEVELS), ("importance", C.c_void_p * MAX_LEVELS),
+                ("importance_rw", C.c_void_p * MAX_LEVELS)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/shine_b200.h
 _vp, _i64, _i32, _u32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_float
 _OCT, _DEC = C.POINTER(ShineOctree), C.POINTER(ShineDecoder)
@@ -65,6 +79,9 @@ SYMBOLS = {
     "shine_sdf_bce_fwd": (C.c_int, [_OCT, _DEC, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _u32, _vp]),
     "shine_sdf_bce_step": (C.c_int, [_OCT, _DEC, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp, _u32, _vp]),
     "shine_reduce_grad_replicas": (C.c_int, [_OCT, _vp]),
+    "shine_mark_touched": (C.c_int, [_OCT, _vp, _i64, C.POINTER(ShineTouched), _vp]),
+    "shine_regularization_apply": (C.c_int, [_OCT, C.POINTER(ShineTouched), C.POINTER(ShineRowTables), _f32, _vp, _i32, _vp]),
+    "shine_importance_accumulate": (C.c_int, [_OCT, C.POINTER(ShineTouched), C.POINTER(ShineRowTables), _i32, _i32, _vp]),
     "shine_adam_step": (C.c_int, [C.POINTER(ShineAdamTensor), _i32, _f32, _f32, _f32, _i32, _i32, _vp]),
     "shine_adam_step_dev": (C.c_int, [C.POINTER(ShineAdamTensor), _i32, _f32, _f32, _f32, _vp, _i32, _vp]),
 }

@@ -6,50 +6,107 @@ snapshots `features_last_frame` / extends `importance_weight`; the optimiser sta
 shine_incre.py:108-109); `iters` x { get_batch -> fused fwd+loss(sum)+bwd -> + lambda_forget * d(reg)/d(features)
 -> Adam }; then `cal_feature_importance` sweeps the frame's pool and accumulates |dL/dfeature| into the importance.
 
-The BCE part is the fused sm_100a step; the regulariser (model/feature_octree.py:246-255) touches only the unique rows of
-the batch and is applied with a handful of torch GPU ops on the (lazily materialised) `hierarchical_indices`.
+The BCE part is the fused sm_100a step; the regulariser (model/feature_octree.py:246-255) and the importance update touch
+only the rows the batch touched: `shine_mark_touched` collects them (bitmap + compact list, no unique()/sort) and
+`shine_regularization_apply` / `shine_importance_accumulate` run over that list.
 """
 from __future__ import annotations
 
-import math
+import ctypes as C
 
 import torch
 
+from . import _abi
 from .config import SHINEConfig
 from .decoder import Decoder
 from .feature_octree import FeatureOctree
 from .trainer import SdfTrainer
 
 
-def add_regularization(trainer: SdfTrainer, octree: FeatureOctree, lambda_forget: float) -> torch.Tensor:
-    """loss += lambda * cal_regularization(); grads += lambda * 2 Omega (f - f_last) on the unique rows of the last batch."""
-    reg = torch.zeros((), device=trainer.flat_grad.device)
-    idx = octree.hierarchical_indices          # bottom-up [N,8] per level, materialised by shine_get_indices
-    for i in range(octree.featured_level_num):
-        k = octree.featured_level_num - i - 1
-        u = idx[i].flatten().unique()           # includes -1 (the trash row), like the reference
-        f = octree.hier_features[k].data
-        diff = f[u] - octree.features_last_frame[k][u]
-        w = octree.importance_weight[k][u]
-        reg = reg + (w * diff * diff).sum()
-        trainer.table_grads[k].index_add_(0, torch.where(u < 0, u + f.shape[0], u), (2.0 * lambda_forget) * w * diff)
+class TouchedRows:
+    """Device scratch of the per-touched-row passes: one bitmap word per 32 rows and a compact row list per level
+    (bottom-up like the C descriptors).  Rebuilt when `octree.update()` re-grows the tables."""
+
+    def __init__(self, octree: FeatureOctree):
+        dev = octree.hier_features[0].device
+        L = octree.featured_level_num
+        self.counts = torch.zeros(L, dtype=torch.int32, device=dev)
+        self.bitmaps, self.rows = [], []
+        self.desc = _abi.ShineTouched()
+        self.rows_sig = tuple(int(p.shape[0]) for p in octree.hier_features)
+        for i in range(L):
+            k = L - i - 1
+            n_rows = int(octree.hier_features[k].shape[0])
+            bm = torch.zeros((n_rows + 31) // 32, dtype=torch.int32, device=dev)
+            rl = torch.empty(n_rows, dtype=torch.int32, device=dev)
+            self.bitmaps.append(bm); self.rows.append(rl)
+            lv = self.desc.lv[i]
+            lv.bitmap, lv.rows = bm.data_ptr(), rl.data_ptr()
+            lv.count = self.counts.data_ptr() + 4 * i
+            lv.capacity = n_rows
+
+    @staticmethod
+    def of(octree: FeatureOctree) -> "TouchedRows":
+        t = getattr(octree, "_touched_rows", None)
+        if t is None or t.rows_sig != tuple(int(p.shape[0]) for p in octree.hier_features) or \
+                t.counts.device != octree.hier_features[0].device:
+            t = TouchedRows(octree)
+            octree._touched_rows = t
+        return t
+
+
+def _row_tables(octree: FeatureOctree, writable: bool) -> _abi.ShineRowTables:
+    aux = _abi.ShineRowTables()
+    L = octree.featured_level_num
+    for i in range(L):
+        k = L - i - 1
+        aux.last[i] = octree.features_last_frame[k].data_ptr()
+        aux.importance[i] = octree.importance_weight[k].data_ptr()
+        aux.importance_rw[i] = octree.importance_weight[k].data_ptr() if writable else None
+    return aux
+
+
+def add_regularization(trainer: SdfTrainer, octree: FeatureOctree, lambda_forget: float, coord=None) -> torch.Tensor:
+    """reg = cal_regularization() over the rows touched by the last batch (model/feature_octree.py:246-255) and
+    grads += 2 lambda Omega (f - f_last) on those rows — two launches (mark, apply), no unique()/sort, nothing dense."""
+    coord = octree._last_coord if coord is None else coord
+    if coord is None:
+        raise _abi.ShineB200Error("add_regularization needs the batch of the last step (octree._last_coord)")
+    dev = trainer.flat_grad.device
+    t = TouchedRows.of(octree)
+    od = octree._descriptor(None, trainer.table_grads)
+    reg = torch.zeros((), device=dev)
+    t.counts.zero_()
+    lib, st = _abi.lib(), _abi.stream_ptr(dev)
+    _abi.check(lib.shine_mark_touched(C.byref(od), _abi.ptr(coord), coord.shape[0], C.byref(t.desc), st),
+               "shine_mark_touched")
+    aux = _row_tables(octree, writable=False)
+    _abi.check(lib.shine_regularization_apply(C.byref(od), C.byref(t.desc), C.byref(aux), 2.0 * lambda_forget,
+                                              _abi.ptr(reg), 1, st), "shine_regularization_apply")
     return reg
 
 
 @torch.no_grad()
 def cal_feature_importance(trainer: SdfTrainer, octree: FeatureOctree, coord_pool, label_pool, bs: int, down_rate: int = 1):
-    """utils/incre_learning.py:8-40 on the fused kernel: importance += |dL/dfeature| per pool stride."""
+    """utils/incre_learning.py:8-40 on the fused kernel: per pool stride, one unweighted step, then
+    importance[u] += |dL/dfeature[u]| over the rows that stride touched (which also re-zeroes their gradients)."""
     n = coord_pool.shape[0]
     interval = bs * down_rate
+    dev = trainer.flat_grad.device
+    t = TouchedRows.of(octree)
+    aux = _row_tables(octree, writable=True)
+    lib, st = _abi.lib(), _abi.stream_ptr(dev)
+    trainer.zero_grad()
     for head in range(0, n, interval):
         c = coord_pool[head:min(head + interval, n):down_rate].contiguous()
         l = label_pool[head:min(head + interval, n):down_rate].contiguous()
-        trainer.zero_grad()
         trainer.forward_backward(c, l, weighted=False)     # utils/incre_learning.py:33: weight=None
-        for k in range(len(octree.importance_weight)):
-            octree.importance_weight[k] += trainer.table_grads[k].abs()
-            octree.importance_weight[k][-1] *= 0
-    trainer.zero_grad()
+        od = octree._descriptor(None, trainer.table_grads)
+        t.counts.zero_()
+        _abi.check(lib.shine_mark_touched(C.byref(od), _abi.ptr(c), c.shape[0], C.byref(t.desc), st), "shine_mark_touched")
+        _abi.check(lib.shine_importance_accumulate(C.byref(od), C.byref(t.desc), C.byref(aux), 1, 1, st),
+                   "shine_importance_accumulate")
+    trainer.zero_grad()          # decoder segment + loss accumulator
 
 
 def run_shine_mapping_incremental(config: SHINEConfig, octree: FeatureOctree, decoder: Decoder, frames, iters=None,
@@ -79,8 +136,7 @@ def run_shine_mapping_incremental(config: SHINEConfig, octree: FeatureOctree, de
             loss = trainer.forward_backward(c, l, w)
             total = loss.clone()
             if config.continual_learning_reg:
-                octree._last_coord, octree._hier_idx = c, []      # the batch whose unique rows are regularised
-                total = total + config.lambda_forget * add_regularization(trainer, octree, config.lambda_forget)
+                total = total + config.lambda_forget * add_regularization(trainer, octree, config.lambda_forget, c)
             trainer.optimizer_step(zero_grad=True)
             if it == 0:
                 first, bce_first = float(total), float(loss)

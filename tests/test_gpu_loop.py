@@ -125,6 +125,8 @@ def test_regularization_and_importance_match_oracle(built_lib):
     g = torch.Generator().manual_seed(5)
     last = [t + 0.01 * torch.randn(t.shape, generator=g).numpy() for t in case["tables"]]
     imp = [torch.rand(t.shape, generator=g).numpy() for t in case["tables"]]
+    for w in imp:
+        w[-1] = 0.0      # reference invariant: the trash row's importance is reset after every pass (utils/incre_learning.py:40)
     octree.features_last_frame = [torch.from_numpy(np.asarray(t, dtype=np.float32)).to(DEV) for t in last]
     octree.importance_weight = [torch.from_numpy(np.asarray(t, dtype=np.float32)).to(DEV) for t in imp]
     coord = torch.from_numpy(case["coord"]).to(DEV); label = torch.from_numpy(case["label"]).to(DEV)
@@ -133,7 +135,13 @@ def test_regularization_and_importance_match_oracle(built_lib):
     tr.zero_grad()
     octree.query_feature(coord)
     lam = 1e3
-    reg = add_regularization(tr, octree, lam)
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        reg = add_regularization(tr, octree, lam)
+        torch.cuda.synchronize()
+    names = [e.key for e in prof.key_averages() if e.device_type == torch.autograd.DeviceType.CUDA]
+    assert any("mark_touched" in k for k in names) and any("touched_rows" in k for k in names), names
+    assert not any(("sort" in k.lower() or "unique" in k.lower() or "radix" in k.lower()) for k in names), names
     assert abs(float(reg) - float(octree.cal_regularization())) <= 1e-5 * abs(float(reg))
     o, odec = oracle_from_case(case)
     o.get_indices(torch.from_numpy(case["coord"]))
