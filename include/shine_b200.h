@@ -203,6 +203,36 @@ int shine_regularization_apply(const shine_octree* oct, const shine_touched* tou
 int shine_importance_accumulate(const shine_octree* oct, const shine_touched* touched, const shine_row_tables* aux,
                                 int32_t zero_grads, int32_t clear_marks, void* stream);
 
+/* ---- multi-GPU exchange (SURVEY.md 8e, 8b export (6); the reference is single-GPU) --------------------------------
+ * One process per GPU.  The map is partitioned by Morton prefix at the coarsest featured level; every rank owns the
+ * rows reachable from its blocks, so corner rows on a face between two blocks exist on both ranks.  Their gradients
+ * are summed through a compact exchange buffer laid out [decoder grads | boundary rows of lv[0] | lv[1] | ...]:
+ * pack -> ONE all-reduce (decoder + boundary) -> unpack. */
+typedef struct shine_boundary_level {
+    float* table;             /* this rank's [rows, F] gradient (or feature) table of the level                 */
+    const int32_t* rows;      /* [count] local rows that are shared with another rank                           */
+    const int32_t* slots;     /* [count] their positions in the level's globally agreed boundary list           */
+    int64_t offset;           /* float offset of the level's segment in the exchange buffer (multiple of 4)     */
+    int32_t count;
+    int32_t reserved;
+} shine_boundary_level;
+typedef struct shine_boundary { shine_boundary_level lv[SHINE_MAX_LEVELS]; } shine_boundary;
+
+/* buf[offset_l + slot * F ..] = table_l[row]   /   table_l[row] = buf[offset_l + slot * F ..] */
+int shine_boundary_pack(const shine_boundary* plan, int32_t num_levels, int32_t feature_dim, float* buf, void* stream);
+int shine_boundary_unpack(const shine_boundary* plan, int32_t num_levels, int32_t feature_dim, float* buf, void* stream);
+
+/* NCCL communicator owned by this library (NCCL is bound with dlopen at run time).  Rank 0 makes the 128-byte
+ * unique id, the caller distributes it (any transport), every rank creates its communicator on `device`. */
+int shine_nccl_unique_id(void* out_id128);
+int shine_nccl_comm_create(const void* id128, int32_t nranks, int32_t rank, int32_t device, void** out_comm);
+int shine_nccl_comm_destroy(void* comm);
+/* In-place sum all-reduce of `count` floats over NVLink, asynchronous on `stream`: the decoder-gradient exchange
+ * that follows the backward (comm is the ncclComm_t made above, or any ncclComm_t of the same NCCL).
+ * NCCL failures return -1000 - ncclResult_t; shine_comm_last_error() has the text. */
+int shine_allreduce_decoder_grads(void* comm, float* buf, int64_t count, void* stream);
+const char* shine_comm_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,15 @@ class ShineRowTables(C.Structure):
                 ("importance_rw", C.c_void_p * MAX_LEVELS)]
 
 
+class ShineBoundaryLevel(C.Structure):
+    _fields_ = [("table", C.c_void_p), ("rows", C.c_void_p), ("slots", C.c_void_p), ("offset", C.c_int64),
+                ("count", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ShineBoundary(C.Structure):
+    _fields_ = [("lv", ShineBoundaryLevel * MAX_LEVELS)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/shine_b200.h
 _vp, _i64, _i32, _u32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_float
 _OCT, _DEC = C.POINTER(ShineOctree), C.POINTER(ShineDecoder)
@@ -82,6 +91,13 @@ SYMBOLS = {
     "shine_mark_touched": (C.c_int, [_OCT, _vp, _i64, C.POINTER(ShineTouched), _vp]),
     "shine_regularization_apply": (C.c_int, [_OCT, C.POINTER(ShineTouched), C.POINTER(ShineRowTables), _f32, _vp, _i32, _vp]),
     "shine_importance_accumulate": (C.c_int, [_OCT, C.POINTER(ShineTouched), C.POINTER(ShineRowTables), _i32, _i32, _vp]),
+    "shine_boundary_pack": (C.c_int, [C.POINTER(ShineBoundary), _i32, _i32, _vp, _vp]),
+    "shine_boundary_unpack": (C.c_int, [C.POINTER(ShineBoundary), _i32, _i32, _vp, _vp]),
+    "shine_nccl_unique_id": (C.c_int, [_vp]),
+    "shine_nccl_comm_create": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(C.c_void_p)]),
+    "shine_nccl_comm_destroy": (C.c_int, [_vp]),
+    "shine_allreduce_decoder_grads": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "shine_comm_last_error": (C.c_char_p, []),
     "shine_adam_step": (C.c_int, [C.POINTER(ShineAdamTensor), _i32, _f32, _f32, _f32, _i32, _i32, _vp]),
     "shine_adam_step_dev": (C.c_int, [C.POINTER(ShineAdamTensor), _i32, _f32, _f32, _f32, _vp, _i32, _vp]),
 }
@@ -117,7 +133,7 @@ LAUNCHES = {"count": 0}   # successful kernel-launching ABI calls (bench.py repo
 def check(rc: int, what: str) -> None:
     LAUNCHES["count"] += 1
     if rc != 0:
-        msg = lib().shine_error_string(rc).decode()
+        msg = (lib().shine_comm_last_error() if rc <= -1000 else lib().shine_error_string(rc)).decode()
         raise ShineB200Error(f"{what} failed: {msg} (code {rc})")
 
 

@@ -22,6 +22,15 @@
 #include "shine_b200.h"
 
 // tuning switches (defaults = the best measured on B200; every alternative is in profiles/r01_summary.md)
+#ifndef SHINE_SECTOR_PROBE
+#define SHINE_SECTOR_PROBE 1  // 1: lane reads key + its 4 corner rows as one 32-byte sector per level; 0: level-split key probes, then ids
+#endif
+#ifndef SHINE_CPASYNC_PREFETCH
+#define SHINE_CPASYNC_PREFETCH 1  // 1: next tile's inputs via cp.async to shared memory; 0: register prefetch
+#endif
+#ifndef SHINE_DW3_TMEM
+#define SHINE_DW3_TMEM 1      // 1: output-layer weight-gradient accumulators parked in TMEM; 0: registers
+#endif
 #ifndef SHINE_GATHER_GROUP
 #define SHINE_GATHER_GROUP 2  // levels whose first-probe sectors are in flight together (register pressure vs parallelism)
 #endif
@@ -528,6 +537,11 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
     // decoder-gradient accumulators: dW2/dW1/db2/db1/dw3 are parked in TMEM (SHINE_ACC_*); only db3 stays in a register
     float db3p = 0.f;
     float loss_acc = 0.f;
+#if !SHINE_DW3_TMEM
+    float dw3r[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { dw3r[j][0] = dw3r[j][1] = 0.f; }
+#endif
 
     float* stage = smem + SmemPlan::STAGE + warp * SmemPlan::kStagePerWarp;   // only touched when DEC_GRAD
     float* stA = stage;                       // [16][kWS]
@@ -545,6 +559,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
     for (int i = 1; i < LMAX; ++i)
         if (i < L && P.oct.lv[i].level != P.oct.lv[0].level - i) consecutive = false;
 
+#if SHINE_CPASYNC_PREFETCH
     // software pipeline, depth 1: the next tile's coordinates / label / weight travel global -> shared memory with
     // cp.async (no registers pinned, nothing to spill) while this tile computes
     float* pre = smem + SmemPlan::PRE + warp * SmemPlan::kPrePerWarp;
@@ -585,6 +600,30 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         __syncwarp();
         prefetch_inputs(tile + warp_stride);
 
+#else
+    // software pipeline, depth 1: the next tile's coordinates / label are in flight (registers) while this tile computes
+    float nx = 0.f, ny = 0.f, nz = 0.f, nlab = 0.f, nwgt = 1.f;
+    bool nvalid = false;
+    auto prefetch_inputs = [&](int tl) {
+        const int64_t p = (int64_t)tl * kTile + g + 8 * odd;
+        nvalid = tl < P.num_tiles && p < P.n;
+        if (nvalid) {
+            nx = __ldg(P.coord + 3 * p); ny = __ldg(P.coord + 3 * p + 1); nz = __ldg(P.coord + 3 * p + 2);
+            if (P.label) nlab = __ldg(P.label + p);
+            if (P.weighted) nwgt = fabsf(__ldg(P.weight + p));   // shine_batch.py:172 abs()
+        }
+    };
+    prefetch_inputs(warp_global);
+
+    for (int tile = warp_global; tile < P.num_tiles; tile += warp_stride) {
+        const int64_t base = (int64_t)tile * kTile;
+        const int64_t myp = base + g + 8 * odd;
+        const bool valid = nvalid;
+        const float x = nx, y = ny, z = nz, lab = nlab, wgt = nwgt;
+        prefetch_inputs(tile + warp_stride);
+
+#endif
+#if SHINE_SECTOR_PROBE
         // ---- hash walk + 8-corner gather + blend, summed over levels (model/feature_octree.py:199-234).
         //      The two lanes of a point split the CORNERS by z bit: lane `half` reads sector `half` of the first-probe
         //      slot of EVERY level with one 256-bit load (key + its 4 corner rows; all levels in flight together), then
@@ -654,6 +693,99 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                 feat[q] = (half ? acc[4 + q] : acc[q]) + recv;
             }
         }
+#else
+        // ---- hash walk (model/feature_octree.py:199-218).  The two lanes of a point split the LEVELS: lane `half`
+        //      probes levels half, half+2, ... (first-probe keys of all its levels in flight together), then the
+        //      pair exchanges slot indices.  Serial dependent probes per lane: 1 instead of L. ----
+        int slot[LMAX];
+        {
+            constexpr int LH = LMAX / 2;
+            const unsigned long long key0 = valid ? morton_of(x, y, z, P.oct.lv[0].level) : 0ull;
+            unsigned long long kq[LH], kf[LH];
+            int mine[LH];
+#pragma unroll
+            for (int j = 0; j < LH; ++j) {
+                const int i = 2 * j + half;
+                mine[j] = -1;
+                if (i < L && valid) {
+                    const shine_level& lv = P.oct.lv[i];
+                    const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
+                    kq[j] = consecutive ? (key0 >> (3 * i)) : morton_of(x, y, z, lv.level);
+                    mine[j] = (int)(hash_key(kq[j]) & (lv.hash_capacity - 1));
+                    kf[j] = __ldg(&slots[mine[j]].key);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < LH; ++j) {
+                const int i = 2 * j + half;
+                if (i < L && valid && kf[j] != kq[j]) {
+                    if (kf[j] == kEmptyKey) {
+                        mine[j] = -1;
+                    } else {   // first-probe collision (rare at load factor <= 0.5): walk on
+                        const shine_level& lv = P.oct.lv[i];
+                        mine[j] = probe_slot_from(reinterpret_cast<const HashSlot*>(lv.hash_slots),
+                                                  lv.hash_capacity - 1, kq[j], (uint32_t)mine[j], 1u);
+                    }
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < LH; ++j) {
+                const int other = __shfl_xor_sync(kFull, mine[j], 2);
+                slot[2 * j] = half ? other : mine[j];
+                slot[2 * j + 1] = half ? mine[j] : other;
+            }
+        }
+
+        // ---- 8-corner gather + blend, summed over levels (model/feature_octree.py:222-234).  The pair splits the
+        //      CORNERS: lane `half` fetches the corners with z bit == half as whole 32-byte rows (one LDG.256 each) and
+        //      blends all 8 channels; the two partial sums are then exchanged so that each lane ends with the 4
+        //      channels of its row-half. ----
+        float feat[4];
+        float pk[kPark];      // [3i..3i+2] = tx,ty,tz of level i (parked in TMEM over the MLP phase)
+        float idp[kIdPark];   // [4i..4i+3] = rows of this lane's corners (z bit == half) of level i, -1 on a miss
+        uint32_t hitmask = 0;
+        {
+            float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < kPark; ++i) pk[i] = 0.f;
+#pragma unroll
+            for (int i = 0; i < kIdPark; ++i) idp[i] = __int_as_float(-1);
+#pragma unroll
+            for (int i = 0; i < LMAX; ++i) {
+                if (i < L && slot[i] >= 0) {
+                    const shine_level& lv = P.oct.lv[i];
+                    const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
+                    hitmask |= 1u << i;
+                    const int4 id4 = ldg_i4(slot_ids(slots, slot[i], half));
+                    idp[4 * i] = __int_as_float(id4.x); idp[4 * i + 1] = __int_as_float(id4.y);
+                    idp[4 * i + 2] = __int_as_float(id4.z); idp[4 * i + 3] = __int_as_float(id4.w);
+                    float r0[8], r1[8], r2[8], r3[8];
+                    ldg_row8(lv.features + (int64_t)id4.x * kF, r0);
+                    ldg_row8(lv.features + (int64_t)id4.y * kF, r1);
+                    ldg_row8(lv.features + (int64_t)id4.z * kF, r2);
+                    ldg_row8(lv.features + (int64_t)id4.w * kF, r3);
+                    Blend b; b.init(x, y, z, lv.level, poly);
+                    pk[3 * i] = b.tx; pk[3 * i + 1] = b.ty; pk[3 * i + 2] = b.tz;
+                    const float wz = half ? b.tz : b.uz;
+                    const float w0 = __fmul_rn(__fmul_rn(b.ux, b.uy), wz), w1 = __fmul_rn(__fmul_rn(b.ux, b.ty), wz);
+                    const float w2 = __fmul_rn(__fmul_rn(b.tx, b.uy), wz), w3 = __fmul_rn(__fmul_rn(b.tx, b.ty), wz);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float a = acc[q];
+                        a = fmaf(w0, r0[q], a); a = fmaf(w1, r1[q], a); a = fmaf(w2, r2[q], a); a = fmaf(w3, r3[q], a);
+                        acc[q] = a;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float send = half ? acc[q] : acc[4 + q];
+                const float recv = __shfl_xor_sync(kFull, send, 2);
+                feat[q] = (half ? acc[4 + q] : acc[q]) + recv;
+            }
+        }
+#endif
         if (TRAIN) {
             if (kPark == 16) tmem_st16(tpark, pk); else tmem_st32(tpark, pk);
             if (kIdPark == 16) tmem_st16(tpark + kPark, idp); else tmem_st32(tpark + kPark, idp);
@@ -760,7 +892,11 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
             dh2[j][0] = h2[j][0] > 0.f ? dp0 * w3a[j] : 0.f; dh2[j][1] = h2[j][1] > 0.f ? dp0 * w3b[j] : 0.f;
             dh2[j][2] = h2[j][2] > 0.f ? dp8 * w3a[j] : 0.f; dh2[j][3] = h2[j][3] > 0.f ? dp8 * w3b[j] : 0.f;
             if (DEC_GRAD) {
+#if SHINE_DW3_TMEM
                 dw3t[j][0] = dp0 * h2[j][0] + dp8 * h2[j][2];  dw3t[j][1] = dp0 * h2[j][1] + dp8 * h2[j][3];
+#else
+                dw3r[j][0] += dp0 * h2[j][0] + dp8 * h2[j][2]; dw3r[j][1] += dp0 * h2[j][1] + dp8 * h2[j][3];
+#endif
                 db2t[j][0] = dh2[j][0] + dh2[j][2];            db2t[j][1] = dh2[j][1] + dh2[j][3];
                 *reinterpret_cast<float2*>(stA + g * kWS + 8 * j + 2 * t) = make_float2(dh2[j][0], dh2[j][1]);
                 *reinterpret_cast<float2*>(stA + (g + 8) * kWS + 8 * j + 2 * t) = make_float2(dh2[j][2], dh2[j][3]);
@@ -812,7 +948,9 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
             for (int j = 0; j < 4; ++j) {
                 db2p[j][0] += db2t[j][0]; db2p[j][1] += db2t[j][1];
                 db1p[j][0] += db1t[j][0]; db1p[j][1] += db1t[j][1];
+#if SHINE_DW3_TMEM
                 dw3p[j][0] += dw3t[j][0]; dw3p[j][1] += dw3t[j][1];
+#endif
             }
             __syncwarp();
             // dW2[n2][k1] += sum_rows dh2[row][n2] * h1[row][k1]
@@ -913,7 +1051,11 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
+#if SHINE_DW3_TMEM
                 float a = db1p[j][q], b = db2p[j][q], c = dw3p[j][q];
+#else
+                float a = db1p[j][q], b = db2p[j][q], c = dw3r[j][q];
+#endif
 #pragma unroll
                 for (int o = 4; o < 32; o <<= 1) {
                     a += __shfl_xor_sync(kFull, a, o); b += __shfl_xor_sync(kFull, b, o); c += __shfl_xor_sync(kFull, c, o);

@@ -31,6 +31,43 @@ def init_from_env(backend: str | None = None):
     return rank, world, local
 
 
+class NcclComm:
+    """NCCL communicator created and driven through the C ABI (`shine_nccl_comm_create`,
+    `shine_allreduce_decoder_grads`): the step's collective does not go through torch.distributed.  The 128-byte unique
+    id travels over whatever process group is already up (set-up only)."""
+
+    def __init__(self, rank: int, world: int, device: torch.device, group=None):
+        import ctypes as C
+        from . import _abi
+        self.rank, self.world, self.device = rank, world, torch.device(device)
+        lib = _abi.lib()
+        uid = (C.c_ubyte * 128)()
+        if rank == 0:
+            _abi.check(lib.shine_nccl_unique_id(uid), "shine_nccl_unique_id")
+        box = [bytes(uid)]
+        if world > 1:
+            dist.broadcast_object_list(box, src=0, group=group)
+        uid = (C.c_ubyte * 128).from_buffer_copy(box[0])
+        comm = C.c_void_p()
+        _abi.check(lib.shine_nccl_comm_create(uid, world, rank, self.device.index or 0, C.byref(comm)),
+                   "shine_nccl_comm_create")
+        self._comm, self._lib, self._abi = comm, lib, _abi
+
+    def all_reduce(self, t: torch.Tensor) -> torch.Tensor:
+        """In-place sum over all ranks, asynchronous on the current stream."""
+        if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+            raise ValueError("NcclComm.all_reduce: contiguous fp32 CUDA tensor expected")
+        self._abi.check(self._lib.shine_allreduce_decoder_grads(self._comm, self._abi.ptr(t), t.numel(),
+                                                                self._abi.stream_ptr(t.device)),
+                        "shine_allreduce_decoder_grads")
+        return t
+
+    def close(self):
+        if self._comm:
+            self._lib.shine_nccl_comm_destroy(self._comm)
+            self._comm = None
+
+
 def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous, balanced slice [begin, end) of an n-point batch for `rank` (sizes differ by at most 1)."""
     base, rem = divmod(n, world)
@@ -106,9 +143,10 @@ def pin_to_gpu_numa_node(local_rank: int) -> dict:
         with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
             cpus = _parse_cpulist(f.read())
         allowed = os.sched_getaffinity(0)
-        cpus = (cpus & allowed) or allowed
-        os.sched_setaffinity(0, cpus)
-        info["cpus"] = len(cpus)
+        cpus = cpus & allowed
+        if len(cpus) >= 4:                      # never squeeze a rank onto a sliver of a cgroup-restricted node
+            os.sched_setaffinity(0, cpus)
+            info["cpus"] = len(cpus)
     except Exception:
         pass
     return info

@@ -117,10 +117,10 @@ class SamplePool:
         return self.coord_pool[index, :], self.sdf_label_pool[index], self.weight_pool[index]
 
 
-def build_scene_map(config: SHINEConfig, octree, n_azimuth: int, n_frames: int = 1, frame_step_m: float = 1.0,
-                    seed: int = 42, device=None, origin_x0: float = 0.0):
-    """Scan the analytic scene from `n_frames` poses along +x, sample every scan, grow the octree from the
-    surface samples (weight > 0; dataset/lidar_dataset.py:212-218) and return the SamplePool."""
+def generate_scans(config: SHINEConfig, n_azimuth: int, n_frames: int = 1, frame_step_m: float = 1.0, seed: int = 42,
+                   device=None, origin_x0: float = 0.0):
+    """Scan the analytic scene from `n_frames` poses along +x and sample every scan like the reference's sampler.
+    -> list of (coord, sdf_label, weight, hits_scaled) per frame."""
     device = device or config.device
     gen = torch.Generator(device=device)
     gen.manual_seed(seed)
@@ -128,14 +128,25 @@ def build_scene_map(config: SHINEConfig, octree, n_azimuth: int, n_frames: int =
     boxes = default_boxes(device)
     boxes[:, 0] += origin_x0
     boxes[:, 3] += origin_x0
-    pool = SamplePool(device)
+    frames = []
     for f in range(n_frames):
         origin = torch.tensor([origin_x0 + f * frame_step_m, 0.0, 0.0], device=device)
         hits = raycast_scene(origin, dirs, boxes, min_range=config.min_range, max_range=config.pc_radius)
         coord, label, weight = sample_rays(hits * config.scale, origin * config.scale, config, gen)
+        frames.append((coord, label, weight, hits * config.scale))
+    return frames
+
+
+def build_scene_map(config: SHINEConfig, octree, n_azimuth: int, n_frames: int = 1, frame_step_m: float = 1.0,
+                    seed: int = 42, device=None, origin_x0: float = 0.0):
+    """Scan the analytic scene from `n_frames` poses along +x, sample every scan, grow the octree from the
+    surface samples (weight > 0; dataset/lidar_dataset.py:212-218) and return the SamplePool."""
+    device = device or config.device
+    pool = SamplePool(device)
+    for coord, label, weight, hits in generate_scans(config, n_azimuth, n_frames, frame_step_m, seed, device, origin_x0):
         if config.octree_from_surface_samples:
             octree.update(coord[weight > 0, :])
         else:
-            octree.update(hits * config.scale)
+            octree.update(hits)
         pool.append(coord, label, weight)
     return pool

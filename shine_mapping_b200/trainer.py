@@ -28,14 +28,17 @@ def _align4(n: int) -> int:
 
 class SdfTrainer:
     def __init__(self, config: SHINEConfig, octree: FeatureOctree, decoder: Decoder, process_group=None,
-                 tf32x1: bool = False, shard_mode: str = "replicated"):
-        """shard_mode (multi-GPU, see dist.py): "replicated" = every rank holds the whole table and a slice of the
-        point batch -> all-reduce the whole flat gradient; "spatial" = every rank owns its own octree block and
-        the samples inside it (BASELINE config 5) -> only the decoder segment is all-reduced."""
+                 tf32x1: bool = False, shard_mode: str = "replicated", boundary=None, comm=None):
+        """shard_mode (multi-GPU, see dist.py / partition.py): "replicated" = every rank holds the whole table and a
+        slice of the point batch -> all-reduce the whole flat gradient; "spatial" = every rank owns a Morton-prefix
+        range of ONE map and the samples inside it (BASELINE config 5) -> ONE all-reduce over
+        [decoder gradients | gradients of the corner rows shared with other ranks] (`boundary`: partition.BoundaryPlan).
+        comm: dist.NcclComm (the C-ABI collective); None = torch.distributed (gloo in the CPU tests)."""
         if shard_mode not in ("replicated", "spatial"):
             raise ValueError(shard_mode)
         self.config, self.octree, self.decoder = config, octree, decoder
         self.shard_mode = shard_mode
+        self.boundary, self.comm = boundary, comm
         # gradient replicas for small hot levels (see FeatureOctree._replicas_for); on by default for big batches
         self.use_replicas = os.environ.get("SHINE_FUSED_REPLICAS", "1") != "0"
         self.group = process_group
@@ -67,9 +70,18 @@ class SdfTrainer:
         for s in sizes:
             offs.append(total)
             total += _align4(s)
-        # + 4 floats at the end: the loss accumulator lives in the same allocation, so zero_grad() clears it for free
-        self._flat_all = torch.zeros(total + 4, dtype=torch.float32, device=dev)
+        # after the decoder segment: the boundary-row exchange slots of a spatial partition (so that ONE in-place
+        # all-reduce covers [decoder | boundary]), then 4 floats for the loss accumulator: zero_grad() clears all of it
+        nb = 0
+        if self.boundary is not None:
+            dec_seg = total - offs[len(tables)]
+            if self.boundary.dec_floats != dec_seg:
+                raise ValueError(f"BoundaryPlan was built for a {self.boundary.dec_floats}-float decoder segment, "
+                                 f"this trainer's is {dec_seg}")
+            nb = self.boundary.total_floats - self.boundary.dec_floats
+        self._flat_all = torch.zeros(total + nb + 4, dtype=torch.float32, device=dev)
         self.flat_grad = self._flat_all[:total]
+        self.exchange = self._flat_all[offs[len(tables)]:total + nb]     # [decoder | boundary rows]
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         self.step_count = 0   # fresh Adam state, like a rebuilt torch optimizer
@@ -86,7 +98,7 @@ class SdfTrainer:
             if p is not None and p.requires_grad:
                 p.grad = g
         self._sig = sig
-        self.loss = self._flat_all[total:total + 1].view(())
+        self.loss = self._flat_all[total + nb:total + nb + 1].view(())
         self._loss_clean = True
 
     def zero_grad(self):
@@ -125,14 +137,29 @@ class SdfTrainer:
             self.octree._reduce_replicas(od, coord.device)
         return self.loss
 
+    def _all_reduce(self, buf):
+        if self.comm is not None:
+            self.comm.all_reduce(buf)
+        elif torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(buf, group=self.group)
+
     def all_reduce_grads(self):
-        """Data-parallel exchange: ONE collective over the flat buffer (sum; the 1/N_global is already in the
-        per-point gradient scale)."""
-        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                      and torch.distributed.get_world_size() > 1):
-            buf = self.dec_flat if self.shard_mode == "spatial" else self.flat_grad
-            if buf.numel() and (self.shard_mode != "spatial" or self._dec_trainable):
-                torch.distributed.all_reduce(buf, group=self.group)
+        """The step's exchange, ONE sum collective (the 1/N_global is already in the per-point gradient scale):
+        replicated -> the whole flat gradient; spatial -> [decoder | rows shared with other ranks]."""
+        world = self.comm.world if self.comm is not None else (
+            torch.distributed.get_world_size(self.group)
+            if torch.distributed.is_available() and torch.distributed.is_initialized() else 1)
+        if world <= 1:
+            return
+        if self.shard_mode == "replicated":
+            self._all_reduce(self.flat_grad)
+            return
+        if self.boundary is not None and self.boundary.total_floats > self.boundary.dec_floats:
+            self.boundary.pack(self.table_grads, self.exchange)
+            self._all_reduce(self.exchange)
+            self.boundary.unpack(self.table_grads, self.exchange)
+        elif self._dec_trainable:
+            self._all_reduce(self.dec_flat)
 
     def optimizer_step(self, zero_grad: bool = True, device_step: bool = False):
         """Dense Adam with the reference's groups (utils/tools.py:57-83) as one multi-tensor launch.  With

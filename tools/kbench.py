@@ -15,6 +15,7 @@ ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--leaf-vox", type=float, default=0.2)
 ap.add_argument("--step-m", type=float, default=2.0)
 ap.add_argument("--sorted", action="store_true", help="Morton-sort the batch (locality experiment)")
+ap.add_argument("--quick", action="store_true", help="only the step / frozen / infer lines")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 from shine_mapping_b200 import Decoder, FeatureOctree, synth
@@ -45,12 +46,13 @@ def timeit(fn, name, bytes_per_pt=None):
 tr3 = SdfTrainer(cfg, octree, decoder)
 tr1 = SdfTrainer(cfg, octree, decoder, tf32x1=True)
 timeit(lambda: tr3.forward_backward(coord, label), "step 3xTF32 dec_grad")
-timeit(lambda: tr1.forward_backward(coord, label), "step 1xTF32 dec_grad")
+if not args.quick: timeit(lambda: tr1.forward_backward(coord, label), "step 1xTF32 dec_grad")
 for p in decoder.parameters(): p.requires_grad = False
 trf3 = SdfTrainer(cfg, octree, decoder); trf1 = SdfTrainer(cfg, octree, decoder, tf32x1=True)
 timeit(lambda: trf3.forward_backward(coord, label), "step 3xTF32 frozen decoder")
-timeit(lambda: trf1.forward_backward(coord, label), "step 1xTF32 frozen decoder")
 timeit(lambda: sdf_infer(octree, decoder, coord), "infer 3xTF32")
+if args.quick: sys.exit(0)
+timeit(lambda: trf1.forward_backward(coord, label), "step 1xTF32 frozen decoder")
 timeit(lambda: sdf_infer(octree, decoder, coord, tf32x1=True), "infer 1xTF32")
 timeit(lambda: sdf_infer(octree, decoder, coord, tcgen05=True), "infer tcgen05 3xTF32")
 feat = torch.empty(n, 8, device=dev); od = octree._descriptor(None, tr3.table_grads, n_points=n)
