@@ -34,6 +34,7 @@ L, F = 4, 8
 BYTES_PER_POINT = 24 + L * 40 + 3 * L * 8 * F * 4   # 3 256 B at L=4, F=8
 GATHER_BYTES_PER_POINT = L * 8 * F * 4               # the forward corner gather alone, 1 024 B
 HBM_FALLBACK_GBS = 6650.0
+C2_POINTS_PER_STEP = 776616   # samples of the C2 scan (64 x 2048 rays, seed 42): the per-GPU step size at every N
 PROFILE_JSON = os.path.join(ROOT, "profiles", "r02_kernel_counters.json")   # ncu-derived per-point counters
 
 
@@ -48,14 +49,53 @@ def workload_config(device):
 
 
 def build_workload(device, rank, world, n_azimuth):
+    """N = 1: the C2 single-scan map."""
     from shine_mapping_b200 import Decoder, FeatureOctree, synth
     cfg = workload_config(device)
+    torch.manual_seed(42)
+    octree, decoder = FeatureOctree(cfg), Decoder(cfg)
+    pool = synth.build_scene_map(cfg, octree, n_azimuth=n_azimuth, n_frames=1, seed=42, device=device)
+    return cfg, octree, decoder, pool
+
+
+SCAN_SPACING_M = 25.0    # multi-GPU map: one scan per GPU, 25 m apart along the street (pc_radius 50 m: they overlap)
+
+
+def build_partitioned_workload(device, rank, world, n_azimuth, n_frames=None):
+    """N > 1: ONE map of `world` overlapping scans, partitioned by Morton prefix at the coarsest featured level into
+    `world` balanced ranges (partition.py).  Every rank generates the same global pool (seeded), keeps the samples of its
+    range, grows its own octree from them; corner rows on the faces between ranges are duplicated and exchanged every
+    step together with the decoder gradients.  -> cfg, octree, decoder, pool, boundary plan, NcclComm."""
+    from shine_mapping_b200 import Decoder, FeatureOctree, dist as sdist, partition, synth
+    import torch.distributed as dist
+    cfg = workload_config(device)
+    cfg.name = "c5_one_map_spatially_partitioned"
     torch.manual_seed(42)   # decoder init identical on every rank (it is replicated)
     octree, decoder = FeatureOctree(cfg), Decoder(cfg)
-    x0 = (rank - (world - 1) / 2.0) * 100.0
-    pool = synth.build_scene_map(cfg, octree, n_azimuth=n_azimuth, n_frames=1, seed=42 + rank, device=device,
-                                 origin_x0=x0)
-    return cfg, octree, decoder, pool
+    n_frames = n_frames or world
+    frames = synth.generate_scans(cfg, n_azimuth, n_frames, SCAN_SPACING_M, 42, device,
+                                  origin_x0=-(n_frames - 1) * SCAN_SPACING_M / 2)
+    coord = torch.cat([f[0] for f in frames]); label = torch.cat([f[1] for f in frames])
+    weight = torch.cat([f[2] for f in frames])
+    del frames
+    level = cfg.tree_level_world - cfg.tree_level_feat + 1
+    bounds = partition.balanced_key_bounds(partition.coarse_keys(coord, level).cpu(), world)
+    box = [bounds]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)          # one agreed split even if RNG streams ever differed
+    bounds, parts = partition.partition_pool(coord, label, weight, cfg, world, bounds=box[0])
+    global_pool = int(coord.shape[0])
+    del coord, label, weight
+    pool = partition.build_rank_map(cfg, octree, parts[rank], device)
+    del parts
+    comm = sdist.NcclComm(rank, world, torch.device(device)) if world > 1 else None
+    plan = partition.BoundaryPlan(rank, partition.gather_corner_keys(octree), cfg.feature_dim,
+                                  partition.decoder_segment_floats(decoder)).to(device)
+    if comm is not None:
+        plan.unify_values(list(octree.hier_features), comm.all_reduce)
+    info = {"global_pool_samples": global_pool, "scans": n_frames, "scan_spacing_m": SCAN_SPACING_M,
+            "boundary_rows": [int(c) for c in plan.counts], "exchange_floats": int(plan.total_floats)}
+    return cfg, octree, decoder, pool, plan, comm, info
 
 
 def shared_config(cfg, n_azimuth, pool_len, n, world, rows):
@@ -395,9 +435,16 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     numa = sdist.pin_to_gpu_numa_node(local) if world > 1 else {"numa_node": sdist.gpu_numa_node(local), "cpus": None}
-    cfg, octree, decoder, pool = build_workload(str(dev), rank, world, args.n_azimuth)
-    n = len(pool) if args.points <= 0 else args.points
-    trainer = SdfTrainer(cfg, octree, decoder, shard_mode="spatial")
+    part_info = None
+    if world > 1:
+        cfg, octree, decoder, pool, plan, comm, part_info = build_partitioned_workload(str(dev), rank, world, args.n_azimuth)
+        # weak scaling: every GPU steps as many points as the single GPU does (one scan's worth), drawn from ITS range
+        n = (args.points if args.points > 0 else C2_POINTS_PER_STEP) if args.global_points <= 0 else args.global_points // world
+        trainer = SdfTrainer(cfg, octree, decoder, shard_mode="spatial", boundary=plan, comm=comm)
+    else:
+        cfg, octree, decoder, pool = build_workload(str(dev), rank, world, args.n_azimuth)
+        n = len(pool) if args.points <= 0 else args.points
+        trainer = SdfTrainer(cfg, octree, decoder, shard_mode="spatial")
     n_global = n * world
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     batches = [pool.get_batch(n, gen) for _ in range(4)]
@@ -451,12 +498,12 @@ def run_ours(args):
         b = pool.get_batch(n, gen)
         host.append(tuple(t.cpu().pin_memory() for t in b[:2]))
     for i in range(max(4, warm)):
-        trainer.submit_host_step(*host[i % n_host], n_norm=n_global).result()
+        trainer.submit_host_step(*host[i % n_host], n_norm=n_global, exchange=world > 1).result()
     sdist.barrier(dev); torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     pending, losses = None, []
     for k in range(args.steps):
-        h = trainer.submit_host_step(*host[k % n_host], n_norm=n_global)
+        h = trainer.submit_host_step(*host[k % n_host], n_norm=n_global, exchange=world > 1)
         if pending is not None:
             losses.append(pending.result())
         pending = h
@@ -473,6 +520,8 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         trainer.step_from_host(*host[k % 4])          # ends with loss.item(): device -> host read
+        if world > 1:
+            trainer.all_reduce_grads(); torch.cuda.synchronize(dev)
         sync_ts.append(time.perf_counter() - t0)
     e2e_sync_sec = sdist.max_over_ranks(statistics.mean(sync_ts), dev)
 
@@ -494,7 +543,10 @@ def run_ours(args):
         "data": "synthetic",
         "config": shared_config(cfg, args.n_azimuth, len(pool), n, world, rows),
         "impl_notes": {"decoder_math": "3xTF32 mma.sync (fp32-grade)",
-                       "parallelism": f"spatial-block x{world} + decoder-grad all-reduce",
+                       "parallelism": "single GPU" if world == 1 else
+                       f"one map, Morton-prefix ranges x{world}; ONE NCCL all-reduce per step over [decoder grads | "
+                       "gradients of corner rows shared between ranges] through the C ABI",
+                       "partition": part_info,
                        "l2": "flushed between timed steps (256 MiB write, not timed)",
                        "timed_step": "grad memset + fused fwd+loss+bwd kernel + replica fold (+ all-reduce when N>1)"},
         # the C2 map (2.75 MB of features) lives in L2: the kernel's physical bound there is the L1TEX LSU data pipe
@@ -546,6 +598,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n-azimuth", type=int, default=2048, help="rays per ring of the synthetic scan (C2: 2048)")
     ap.add_argument("--points", type=int, default=0, help="points per step per GPU (default: the whole scan)")
+    ap.add_argument("--global-points", type=int, default=0,
+                    help="N>1 only: GLOBAL points per step, split over the ranks (BASELINE configs[4]: 1048576)")
     ap.add_argument("--ref-sample", type=int, default=0,
                     help="points per oracle step: reference arm default 0 = the whole step (same config as ours); "
                          "cpu_baseline / parity legs of our arm default to 100000")

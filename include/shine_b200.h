@@ -165,6 +165,21 @@ int shine_adam_step(const shine_adam_tensor* tensors, int32_t count, float beta1
 int shine_adam_step_dev(const shine_adam_tensor* tensors, int32_t count, float beta1, float beta2, float eps,
                         void* state, int32_t zero_grad, void* stream);
 
+/* ---- the step with `ekional_loss_on` (config/kitti/kitti_batch.yaml:46) as one kernel ---------------------------------
+ * Replaces shine_batch.py:119-142,172-185,208-209 + utils/tools.py:175-185 (autograd.grad(pred, coord, create_graph=True)
+ * and the double backward through gather, decoder and loss):
+ *   g = sigma * d pred / d coord;   L = sdf_bce_loss(pred, label) + weight_e * mean_{weight > 0} (1 - |g|)^2
+ * Accumulates dL/d(tables) into lv[i].feature_grads and dL/d(decoder) into dec->g* (both terms).
+ *   weight     [n]: sign marks surface (+) / free-space (-) samples (shine_batch.py:137); |weight| multiplies the BCE
+ *              term only with SHINE_FLAG_WEIGHTED
+ *   n_surface  device int32: number of samples with weight > 0 (shine_count_positive); 0 -> no eikonal contribution
+ *   out_pred [n] / out_grad [n,3] (g) may be NULL; out_loss (+=) BCE part; out_eikonal (+=) the mean, without weight_e */
+int shine_count_positive(const float* values, int64_t n, int32_t* out_count, void* stream);
+int shine_sdf_bce_eikonal_step(const shine_octree* oct, const shine_decoder* dec, const float* coord,
+                               const float* label, const float* weight, int64_t n, float sigma, float loss_scale,
+                               float weight_e, const int32_t* n_surface, float* out_pred, float* out_grad,
+                               float* out_loss, float* out_eikonal, uint32_t flags, void* stream);
+
 /* ---- continual-learning terms of the incremental loop (BASELINE config 4) ---------------------------------------
  * The reference finds the rows a batch touched with `hierarchical_indices[i].flatten().unique()` (a sort per level
  * per step, model/feature_octree.py:251) and then works on dense [rows, F] tensors.  Here the touched rows of a batch

@@ -10,8 +10,9 @@ checkpoint in the reference's format.  What differs: the body of an iteration is
 
 Out of scope here: dataset I/O (open3d), meshing, visualiser, wandb.  `pool` is anything with the
 `get_batch(bs)` contract of LiDARDataset (dataset/lidar_dataset.py:431-448); `synth.build_scene_map` provides one.
-`ekional_loss_on` runs on the class surface (query_feature is differentiable w.r.t. the coordinates, twice); normal /
-consistency / semantic / ray losses are rejected explicitly.
+`ekional_loss_on` is one fused kernel (`shine_sdf_bce_eikonal_step`; the class surface supports the reference's
+autograd recipe too: query_feature is differentiable w.r.t. the coordinates, twice); normal / consistency / semantic /
+ray losses are rejected explicitly.
 """
 from __future__ import annotations
 
@@ -52,9 +53,17 @@ def save_checkpoint(octree, decoder, trainer, run_path, name, iters):
                os.path.join(run_path, f"{name}.pth"))
 
 
+def eikonal_iteration_fused(config: SHINEConfig, trainer: SdfTrainer, coord, sdf_label, weight, grad_out=None):
+    """Loop body with ekional_loss_on (reference shine_batch.py:119-120,137-142,172-185,208-209) as one fused launch
+    (`SdfTrainer.forward_backward_eikonal`).  -> (total loss, eikonal mean) device scalars."""
+    bce, eik = trainer.forward_backward_eikonal(coord, sdf_label, weight, grad_out=grad_out)
+    return bce + config.weight_e * eik, eik
+
+
 def eikonal_iteration(config: SHINEConfig, octree: FeatureOctree, decoder: Decoder, trainer: SdfTrainer, coord, sdf_label,
                       weight):
-    """Loop body with ekional_loss_on (reference shine_batch.py:119-120,137-142,172-185,208-209) on the class surface:
+    """The same loop body on the CLASS surface, call for call like the reference (kept as the drop-in path and as the
+    cross-check of the fused kernel):
     `query_feature` is differentiable w.r.t. the coordinates (shine_query_coord_grad) and that gradient is itself
     differentiable (tangent kernels), so the reference's get_gradient(create_graph=True) recipe works as is.  Gradients
     accumulate into the trainer's flat buffer (param.grad are views of it)."""
@@ -85,7 +94,10 @@ class _GraphedIteration:
 
     def _body(self):
         coord, sdf_label, weight = self.pool.get_batch(self.bs)
-        self.trainer.forward_backward(coord, sdf_label, weight)
+        if self.trainer.config.ekional_loss_on:
+            self.trainer.forward_backward_eikonal(coord, sdf_label, weight)
+        else:
+            self.trainer.forward_backward(coord, sdf_label, weight)
         self.trainer.optimizer_step(zero_grad=True, device_step=True)
 
     def run(self):
@@ -119,8 +131,6 @@ def run_shine_mapping_batch(config: SHINEConfig, octree: FeatureOctree, decoder:
     iters = config.iters if iters is None else iters
     if use_cuda_graph is None:
         use_cuda_graph = world == 1
-    if config.ekional_loss_on:
-        use_cuda_graph = False
     graphed = _GraphedIteration(trainer, pool, config.bs) if (use_cuda_graph and world == 1) else None
     trainer.zero_grad()
     losses = {}
@@ -134,7 +144,7 @@ def run_shine_mapping_batch(config: SHINEConfig, octree: FeatureOctree, decoder:
             graphed.run()
         elif config.ekional_loss_on:
             coord, sdf_label, weight = pool.get_batch(config.bs)
-            eikonal_iteration(config, octree, decoder, trainer, coord, sdf_label, weight)
+            trainer.forward_backward_eikonal(coord, sdf_label, weight, n_norm=config.bs * world)
             trainer.all_reduce_grads()
             trainer.optimizer_step(zero_grad=True)
         else:

@@ -228,33 +228,6 @@ __global__ void __launch_bounds__(256) query_bwd_kernel(const __grid_constant__ 
 // coordinate derivatives of query_feature (eikonal / normal terms; reference utils/tools.py:175-185)
 // ------------------------------------------------------------------------------------------------------
 
-// t and dt/dx of one axis: t = smoothstep(frac(res*(0.5x+0.5))) or the linear fraction; dt/dx = t'(d) * res * 0.5
-__device__ __forceinline__ void axis_td(float x, float res, bool poly, float& t, float& dt) {
-    const float c = __fmul_rn(res, __fmaf_rn(x, 0.5f, 0.5f));
-    const float d = c - truncf(c);
-    const float s = res * 0.5f;
-    if (!poly) { t = d; dt = s; return; }
-    const float d2 = __fmul_rn(d, d);
-    t = __fsub_rn(__fmul_rn(3.0f, d2), __fmul_rn(2.0f, __fmul_rn(d2, d)));
-    dt = (6.0f * d - 6.0f * d2) * s;
-}
-
-struct BlendD {   // weights of model/feature_octree.py:186-193 and their derivatives w.r.t. x, y, z
-    float t[3], u[3], dt[3];
-    __device__ __forceinline__ void init(float x, float y, float z, int level, bool poly) {
-        const float res = (float)(1u << level);
-        axis_td(x, res, poly, t[0], dt[0]); axis_td(y, res, poly, t[1], dt[1]); axis_td(z, res, poly, t[2], dt[2]);
-#pragma unroll
-        for (int a = 0; a < 3; ++a) u[a] = 1.0f - t[a];
-    }
-    // dw_c/da for a = 0,1,2
-    __device__ __forceinline__ void dw(int c, float (&g)[3]) const {
-        const float X = (c & 4) ? t[0] : u[0], Y = (c & 2) ? t[1] : u[1], Z = (c & 1) ? t[2] : u[2];
-        const float dX = (c & 4) ? dt[0] : -dt[0], dY = (c & 2) ? dt[1] : -dt[1], dZ = (c & 1) ? dt[2] : -dt[2];
-        g[0] = dX * Y * Z; g[1] = X * dY * Z; g[2] = X * Y * dZ;
-    }
-};
-
 // MODE 0: coord_grad   1: tangent_fwd   2: tangent_bwd
 template <int LP, int MODE>
 __global__ void __launch_bounds__(256) query_tangent_kernel(const __grid_constant__ shine_octree oct,
@@ -312,55 +285,6 @@ __global__ void __launch_bounds__(256) query_tangent_kernel(const __grid_constan
     } else if (MODE == 1) {
         if (valid) *reinterpret_cast<float4*>(out + p * F + 4 * part) = acc;
     }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// tensor-core helpers: mma.sync m16n8k8 TF32, fp32 accumulate, optional 3xTF32 error compensation
-// ------------------------------------------------------------------------------------------------------
-
-__device__ __forceinline__ uint32_t f2tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    hi = f2tf32(x);
-    lo = f2tf32(x - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// A operand: fp32 values in A-fragment order, split on demand.  NTF == 3: D += Al*Bh + Ah*Bl + Ah*Bh.
-// activation split for 3xTF32: hi = x with the low 13 mantissa bits cleared (1 LOP), lo = x - hi (exact; the MMA
-// reads its top 19 bits).  x*w = hi*wh + hi*wl + lo*wh + O(2^-20 |x w|): same order as the cvt.rna split, one
-// instruction less per element.
-__device__ __forceinline__ void split_fast(float x, uint32_t& hi, uint32_t& lo) {
-    hi = __float_as_uint(x) & 0xFFFFE000u;
-    lo = __float_as_uint(x - __uint_as_float(hi));
-}
-template <int NTF>
-struct AFrag {
-    uint32_t hi[4], lo[4];
-    __device__ __forceinline__ void set(float a0, float a1, float a2, float a3) {
-        if (NTF == 3) {
-            split_fast(a0, hi[0], lo[0]); split_fast(a1, hi[1], lo[1]);
-            split_fast(a2, hi[2], lo[2]); split_fast(a3, hi[3], lo[3]);
-        } else {
-            hi[0] = f2tf32(a0); hi[1] = f2tf32(a1); hi[2] = f2tf32(a2); hi[3] = f2tf32(a3);
-        }
-    }
-};
-template <int NTF>
-__device__ __forceinline__ void mma3(float (&d)[4], const AFrag<NTF>& a, uint2 bh, uint2 bl) {
-    if (NTF == 3) {
-        mma_tf32(d, a.lo, bh.x, bh.y);
-        mma_tf32(d, a.hi, bl.x, bl.y);
-    }
-    mma_tf32(d, a.hi, bh.x, bh.y);
 }
 
 // row-half layout (this lane: 4 channels of its own point) -> A fragment of the 16x8 tile.

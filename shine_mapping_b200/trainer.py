@@ -137,6 +137,37 @@ class SdfTrainer:
             self.octree._reduce_replicas(od, coord.device)
         return self.loss
 
+    def forward_backward_eikonal(self, coord, sdf_label, weight, n_norm=None, pred_out=None, grad_out=None):
+        """The step with `ekional_loss_on` (reference shine_batch.py:119-142,172-185,208-209) as ONE launch
+        (`shine_sdf_bce_eikonal_step`): BCE + weight_e * mean over surface samples of (1 - |sigma d pred/d coord|)^2,
+        gradients of both terms accumulated into the flat buffer.  -> (bce loss, eikonal mean) device scalars;
+        the loop's total loss is bce + config.weight_e * eikonal."""
+        self._sync()
+        cfg = self.config
+        n = coord.shape[0]
+        dev = coord.device
+        weighted = bool(cfg.loss_weight_on)
+        flags = (_abi.FLAG_REDUCTION_SUM if cfg.loss_reduction == "sum" else 0) | (_abi.FLAG_WEIGHTED if weighted else 0)
+        scale = 1.0 if cfg.loss_reduction == "sum" else 1.0 / float(n_norm if n_norm else n)
+        aux = getattr(self, "_eik_aux", None)
+        if aux is None or aux[0].device != dev:
+            aux = (torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.float32, device=dev))
+            self._eik_aux = aux
+        n_surface, eik = aux
+        n_surface.zero_(); eik.zero_()
+        if not self._loss_clean:
+            self.loss.zero_()
+        self._loss_clean = False
+        od = self.octree._descriptor(None, self.table_grads)
+        dd = self.decoder.c_descriptor(self.dec_grads if self._dec_trainable else None)
+        lib, st = _abi.lib(), _abi.stream_ptr(dev)
+        _abi.check(lib.shine_count_positive(_abi.ptr(weight), n, _abi.ptr(n_surface), st), "shine_count_positive")
+        _abi.check(lib.shine_sdf_bce_eikonal_step(
+            C.byref(od), C.byref(dd), _abi.ptr(coord), _abi.ptr(sdf_label), _abi.ptr(weight), n, float(self.sigma), scale,
+            float(cfg.weight_e), _abi.ptr(n_surface), _abi.ptr(pred_out), _abi.ptr(grad_out), _abi.ptr(self.loss),
+            _abi.ptr(eik), flags, st), "shine_sdf_bce_eikonal_step")
+        return self.loss, eik.view(())
+
     def _all_reduce(self, buf):
         if self.comm is not None:
             self.comm.all_reduce(buf)
@@ -251,7 +282,8 @@ class SdfTrainer:
             self._event.synchronize()
             return float(self._loss_host.item())
 
-    def submit_host_step(self, coord_h, label_h, weight_h=None, n_norm=None, optimizer: bool = False):
+    def submit_host_step(self, coord_h, label_h, weight_h=None, n_norm=None, optimizer: bool = False,
+                         exchange: bool = False):
         """Asynchronous variant of `step_from_host` for loops that do not need step k's loss before building step k+1
         (the reference loop reads the loss only for logging, shine_batch.py:215-226).  Two device staging slots: the
         host->device copy of this batch runs on a copy stream while the previous step's kernels run on the main stream;
@@ -284,12 +316,13 @@ class SdfTrainer:
         self.zero_grad()
         self.forward_backward(slot["coord"][:n], slot["label"][:n], slot["weight"][:n] if weighted else None,
                               n_norm=n_norm or n)
+        if exchange or optimizer:
+            self.all_reduce_grads()
         slot["loss_h"].copy_(self.loss.view(1), non_blocking=True)
         done = torch.cuda.Event()
         done.record(main)
         slot["free"] = done
         if optimizer:
-            self.all_reduce_grads()
             self.optimizer_step(zero_grad=False)
         return SdfTrainer.HostStepHandle(done, slot["loss_h"])
 

@@ -196,6 +196,88 @@ def test_eikonal_matches_reference_golden():
         assert np.abs(p.grad.cpu().numpy() - want).max() <= 1e-3 * np.abs(want).max() + 1e-9
 
 
+def _fused_eikonal(case, weight_e):
+    from shine_mapping_b200 import SdfTrainer
+    cfg, octree, dec = build_cuda_models(case, DEV)
+    cfg.ekional_loss_on, cfg.weight_e = True, weight_e
+    coord = torch.from_numpy(case["coord"]).to(DEV); label = torch.from_numpy(case["label"]).to(DEV)
+    weight = torch.from_numpy(case["weight"]).to(DEV)
+    tr = SdfTrainer(cfg, octree, dec)
+    tr.zero_grad()
+    g = torch.empty(coord.shape[0], 3, device=DEV)
+    bce, eik = tr.forward_backward_eikonal(coord, label, weight, grad_out=g)
+    torch.cuda.synchronize()
+    return tr, dec, float(bce) + weight_e * float(eik), float(eik), g.cpu().numpy()
+
+
+@pytest.mark.parametrize("levels,poly", [(2, True), (3, False), (4, True)])
+def test_fused_eikonal_step_matches_oracle(levels, poly):
+    """ONE launch (shine_sdf_bce_eikonal_step) against the oracle's autograd double backward."""
+    from oracle import shine_oracle as orc
+    from tests.parity_utils import oracle_from_case
+    case = make_case(n_points=2000, n_batch=1500, feat_levels=levels, seed=100 + levels, poly=poly)
+    tr, dec, total, eik, g = _fused_eikonal(case, 0.1)
+    o, odec = oracle_from_case(case)
+    want = orc.train_step_eikonal(o, odec, torch.from_numpy(case["coord"]), torch.from_numpy(case["label"]),
+                                  torch.from_numpy(case["weight"]), case["cfg"]["sigma"], 0.1)
+    gw = want["g"].numpy()
+    assert np.abs(g - gw).max() <= 1e-4 * np.abs(gw).max() + 1e-7
+    assert abs(eik - float(want["eikonal"])) <= 1e-4 * abs(float(want["eikonal"])) + 1e-7
+    assert abs(total - float(want["loss"])) <= 1e-4 * abs(float(want["loss"]))
+    for k, gt in enumerate(want["table_grads"]):
+        got = tr.table_grads[k].cpu().numpy()
+        assert np.abs(got - gt.numpy())[:-1].max() <= 1e-3 * np.abs(gt.numpy()).max() + 1e-9, k
+    for name, gd in zip(DEC_KEYS, tr.dec_grads):
+        gt = want["dec_grads"][name].numpy()
+        assert np.abs(gd.cpu().numpy() - gt).max() <= 1e-3 * np.abs(gt).max() + 1e-9, name
+
+
+def test_fused_eikonal_step_matches_reference_golden_and_beats_class_surface():
+    """The fused entry against the outputs of the reference's own classes (tests/golden/ref_eikonal_l3.npz), and its
+    time against the class-surface composition (query kernels + cuBLAS + autograd double backward)."""
+    import json
+    import os
+    from shine_mapping_b200 import SdfTrainer
+    from shine_mapping_b200.batch_loop import eikonal_iteration
+    from tests.parity_utils import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "ref_eikonal_l3.npz"))
+    cfg_j = json.loads(str(z["cfg_json"]))
+    case = {"cfg": cfg_j, "frames": [z["frame_0"]], "tables": [z[f"table_{k}"] for k in range(cfg_j["tree_level_feat"])],
+            "dec": {k: z["dec_" + k] for k in DEC_KEYS}, "coord": z["coord"], "label": z["label"], "weight": z["weight"]}
+    tr, dec, total, eik, g = _fused_eikonal(case, cfg_j["weight_e"])
+    assert np.abs(g - z["exp_g"]).max() <= 1e-4 * np.abs(z["exp_g"]).max() + 1e-7
+    assert abs(eik - float(z["exp_eikonal"])) <= 1e-4 * abs(float(z["exp_eikonal"]))
+    assert abs(total - float(z["exp_loss"])) <= 1e-4 * abs(float(z["exp_loss"]))
+    for k in range(cfg_j["tree_level_feat"]):
+        want = z[f"exp_tgrad_{k}"]
+        assert np.abs(tr.table_grads[k].cpu().numpy() - want)[:-1].max() <= 1e-3 * np.abs(want).max() + 1e-9
+    for name, gd in zip(DEC_KEYS, tr.dec_grads):
+        want = z["exp_dgrad_" + name]
+        assert np.abs(gd.cpu().numpy() - want).max() <= 1e-3 * np.abs(want).max() + 1e-9
+    # timing at the KITTI batch size (config/kitti/kitti_batch.yaml: batch_size 16384)
+    big = make_case(n_points=3000, n_batch=16384, feat_levels=4, seed=7)
+    cfg, octree, dec2 = build_cuda_models(big, DEV)
+    cfg.ekional_loss_on, cfg.weight_e = True, 0.1
+    coord = torch.from_numpy(big["coord"]).to(DEV); label = torch.from_numpy(big["label"]).to(DEV)
+    weight = torch.from_numpy(big["weight"]).to(DEV)
+    tr2 = SdfTrainer(cfg, octree, dec2)
+
+    def timed(fn, reps=10):
+        for _ in range(3):
+            tr2.zero_grad(); fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            tr2.zero_grad(); fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    t_fused = timed(lambda: tr2.forward_backward_eikonal(coord, label, weight))
+    t_class = timed(lambda: eikonal_iteration(cfg, octree, dec2, tr2, coord, label, weight))
+    print(f"eikonal step, {coord.shape[0]} points: fused {t_fused:.3f} ms, class surface {t_class:.3f} ms, x{t_class / t_fused:.1f}")
+    assert t_class > 2.0 * t_fused
+
+
 def test_points_to_morton_bit_exact():
     from shine_mapping_b200 import _abi
     from oracle import shine_oracle as orc
