@@ -606,6 +606,7 @@ def main():
     ap.add_argument("--hbm-frames", type=int, default=100, help="frames of the HBM-bound leg's map")
     ap.add_argument("--hbm-points", type=int, default=1 << 20, help="points per step of the HBM-bound leg")
     ap.add_argument("--no-hbm-leg", action="store_true")
+    ap.add_argument("--hbm-only", action="store_true", help="run only the HBM-bound leg and print its object (ncu target)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-profiler", action="store_true", help="cudaProfilerStart/Stop around the timed steps")
     args = ap.parse_args()
@@ -617,6 +618,11 @@ def main():
         if int(os.environ.get("LOCAL_RANK", "0")) == 0:
             with contextlib.redirect_stdout(sys.stderr):      # stdout carries exactly one JSON line
                 ge.build()
+        if args.hbm_only:
+            dev = torch.device("cuda", 0)
+            torch.cuda.set_device(dev)
+            print(json.dumps(hbm_leg(args, dev, peaks()[0])), flush=True)
+            return
         run_ours(args)
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             torch.distributed.destroy_process_group()

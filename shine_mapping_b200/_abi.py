@@ -70,6 +70,21 @@ class ShineBoundary(C.Structure):
     _fields_ = [("lv", ShineBoundaryLevel * MAX_LEVELS)]
 
 
+class ShineBuildLevel(C.Structure):
+    _fields_ = [("node_slots", C.c_void_p), ("corner_slots", C.c_void_p), ("frame_node_set", C.c_void_p),
+                ("frame_corner_set", C.c_void_p), ("new_node_keys", C.c_void_p), ("node_ids_out", C.c_void_p),
+                ("corner_morton_out", C.c_void_p),
+                ("node_capacity", C.c_uint32), ("corner_capacity", C.c_uint32), ("frame_node_set_capacity", C.c_uint32),
+                ("frame_corner_set_capacity", C.c_uint32),
+                ("level", C.c_int32), ("nodes_before", C.c_int32), ("rows_before", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ShineBuild(C.Structure):
+    _fields_ = [("num_levels", C.c_int32), ("max_level", C.c_int32), ("new_node_count", C.c_void_p),
+                ("new_corner_count", C.c_void_p), ("new_corner_total", C.c_void_p), ("new_corner_keys", C.c_void_p),
+                ("lv", ShineBuildLevel * MAX_LEVELS)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/shine_b200.h
 _vp, _i64, _i32, _u32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_float
 _OCT, _DEC = C.POINTER(ShineOctree), C.POINTER(ShineDecoder)
@@ -88,6 +103,13 @@ SYMBOLS = {
     "shine_sdf_bce_fwd": (C.c_int, [_OCT, _DEC, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _u32, _vp]),
     "shine_sdf_bce_step": (C.c_int, [_OCT, _DEC, _vp, _vp, _vp, _i64, _f32, _f32, _vp, _vp, _vp, _u32, _vp]),
     "shine_reduce_grad_replicas": (C.c_int, [_OCT, _vp]),
+    "shine_octree_frame_nodes": (C.c_int, [C.POINTER(ShineBuild), _vp, _i64, _vp]),
+    "shine_octree_frame_corners": (C.c_int, [C.POINTER(ShineBuild), _i32, _vp]),
+    "shine_octree_sort_scratch_bytes": (C.c_int64, [_i32]),
+    "shine_octree_sort_corners": (C.c_int, [_vp, _vp, _i32, _vp, _i64, _vp]),
+    "shine_octree_assign_rows": (C.c_int, [C.POINTER(ShineBuild), _vp, _i32, _vp]),
+    "shine_octree_fill_nodes": (C.c_int, [C.POINTER(ShineBuild), _i32, _vp, _vp]),
+    "shine_octree_corner_rehash": (C.c_int, [_vp, _u32, _vp, _i64, _vp]),
     "shine_count_positive": (C.c_int, [_vp, _i64, _vp, _vp]),
     "shine_sdf_bce_eikonal_step": (C.c_int, [_OCT, _DEC, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _u32, _vp]),
     "shine_mark_touched": (C.c_int, [_OCT, _vp, _i64, C.POINTER(ShineTouched), _vp]),

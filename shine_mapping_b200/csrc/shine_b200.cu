@@ -22,11 +22,17 @@
 #include "shine_b200.h"
 
 // tuning switches (defaults = the best measured on B200; every alternative is in profiles/r01_summary.md)
-#ifndef SHINE_SECTOR_PROBE
-#define SHINE_SECTOR_PROBE 1  // 1: lane reads key + its 4 corner rows as one 32-byte sector per level; 0: level-split key probes, then ids
+// Front-end of the fused kernel (A/B on B200, profiles/r02_summary.md): reading key + 4 corner rows as one 32-byte
+// sector per level (every lane probes every level) wins for inference (0.140 -> 0.132 ms) but costs the training
+// kernel 12 % more instructions (0.296 -> 0.333 ms); the level-split key probe + ids load is kept there.
+#ifndef SHINE_SECTOR_PROBE_TRAIN
+#define SHINE_SECTOR_PROBE_TRAIN 0
+#endif
+#ifndef SHINE_SECTOR_PROBE_INFER
+#define SHINE_SECTOR_PROBE_INFER 1
 #endif
 #ifndef SHINE_CPASYNC_PREFETCH
-#define SHINE_CPASYNC_PREFETCH 1  // 1: next tile's inputs via cp.async to shared memory; 0: register prefetch
+#define SHINE_CPASYNC_PREFETCH 0  // 1: next tile's inputs via cp.async to shared memory; 0: register prefetch (timing-neutral)
 #endif
 #ifndef SHINE_DW3_TMEM
 #define SHINE_DW3_TMEM 1      // 1: output-layer weight-gradient accumulators parked in TMEM; 0: registers
@@ -453,6 +459,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         SHINE_ACC_STORE(tacc);
     }
 
+    constexpr bool kSectorProbe = TRAIN ? (SHINE_SECTOR_PROBE_TRAIN != 0) : (SHINE_SECTOR_PROBE_INFER != 0);
     const bool poly = P.oct.poly_interp != 0;
     const int L = P.oct.num_levels;
     const float up = (TRAIN && P.d_loss) ? __ldg(P.d_loss) : 1.0f;
@@ -547,17 +554,17 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         prefetch_inputs(tile + warp_stride);
 
 #endif
-#if SHINE_SECTOR_PROBE
+        float feat[4];
+        float pk[kPark];      // [3i..3i+2] = tx,ty,tz of level i (parked in TMEM over the MLP phase)
+        float idp[kIdPark];   // [4i..4i+3] = rows of this lane's corners (z bit == half) of level i, -1 on a miss
+        uint32_t hitmask = 0;
+        if constexpr (kSectorProbe) {
         // ---- hash walk + 8-corner gather + blend, summed over levels (model/feature_octree.py:199-234).
         //      The two lanes of a point split the CORNERS by z bit: lane `half` reads sector `half` of the first-probe
         //      slot of EVERY level with one 256-bit load (key + its 4 corner rows; all levels in flight together), then
         //      fetches those rows whole (one LDG.256 each; the pair's two loads of one instruction hit z-neighbours =
         //      consecutive table rows, usually one 128-byte line) and blends all 8 channels.  The partial sums are
         //      exchanged so that each lane ends with the 4 channels of its row-half. ----
-        float feat[4];
-        float pk[kPark];      // [3i..3i+2] = tx,ty,tz of level i (parked in TMEM over the MLP phase)
-        float idp[kIdPark];   // [4i..4i+3] = rows of this lane's corners (z bit == half) of level i, -1 on a miss
-        uint32_t hitmask = 0;
         {
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -617,7 +624,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                 feat[q] = (half ? acc[4 + q] : acc[q]) + recv;
             }
         }
-#else
+        } else {
         // ---- hash walk (model/feature_octree.py:199-218).  The two lanes of a point split the LEVELS: lane `half`
         //      probes levels half, half+2, ... (first-probe keys of all its levels in flight together), then the
         //      pair exchanges slot indices.  Serial dependent probes per lane: 1 instead of L. ----
@@ -665,10 +672,6 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         //      CORNERS: lane `half` fetches the corners with z bit == half as whole 32-byte rows (one LDG.256 each) and
         //      blends all 8 channels; the two partial sums are then exchanged so that each lane ends with the 4
         //      channels of its row-half. ----
-        float feat[4];
-        float pk[kPark];      // [3i..3i+2] = tx,ty,tz of level i (parked in TMEM over the MLP phase)
-        float idp[kIdPark];   // [4i..4i+3] = rows of this lane's corners (z bit == half) of level i, -1 on a miss
-        uint32_t hitmask = 0;
         {
             float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -709,7 +712,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                 feat[q] = (half ? acc[4 + q] : acc[q]) + recv;
             }
         }
-#endif
+        }
         if (TRAIN) {
             if (kPark == 16) tmem_st16(tpark, pk); else tmem_st32(tpark, pk);
             if (kIdPark == 16) tmem_st16(tpark + kPark, idp); else tmem_st32(tpark + kPark, idp);

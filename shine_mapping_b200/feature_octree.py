@@ -94,6 +94,9 @@ class _LevelState:
         self.hash = None          # uint8 [capacity * 64] device tensor
         self.hash_capacity = 0
         self.hash_count = 0       # nodes already inserted
+        self.corner_hash = None   # int64 [capacity * 2] device tensor (16-byte slots {lexicographic key, row}), CUDA build
+        self.corner_hash_capacity = 0
+        self.corner_hash_count = 0
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -258,6 +261,7 @@ class FeatureOctree(nn.Module):
             cp = _LevelState.__new__(_LevelState)
             cp.__dict__.update(st.__dict__)
             cp.hash, cp.hash_capacity, cp.hash_count = None, 0, 0
+            cp.corner_hash, cp.corner_hash_capacity, cp.corner_hash_count = None, 0, 0
             levels.append(cp)
         state["_levels"] = levels
         return state
@@ -271,6 +275,7 @@ class FeatureOctree(nn.Module):
                          "corner_morton_by_row"):
                 setattr(st, name, fn(getattr(st, name)))
             st.hash, st.hash_capacity, st.hash_count = None, 0, 0
+            st.corner_hash, st.corner_hash_capacity, st.corner_hash_count = None, 0, 0
         self.importance_weight = [fn(t) for t in self.importance_weight]
         self.features_last_frame = [fn(t) for t in self.features_last_frame]
         self._grad_scratch, self._desc_cache, self._last_coord, self._hier_idx = {}, {}, None, []
@@ -321,6 +326,12 @@ class FeatureOctree(nn.Module):
         last (:139-142,153-156); each new node stores its 8 corner rows (:162-166)."""
         dev = self.device
         pts = surface_points.to(dev)
+        if pts.is_cuda:
+            return self._update_cuda(pts.float().contiguous(), incremental_on)
+        # CPU tensors: host-side restatement with torch ops (the query kernels refuse CPU tensors anyway; this path
+        # exists so that table numbering can be checked against the oracle without a GPU)
+        for st in self._levels:
+            self._refresh_sorted(st)
         leaf = torch.unique(points_to_morton(quantize_points(pts, self.max_level)))
         for i in range(self.max_level + 1):
             if i < self.free_level_num:
@@ -375,6 +386,159 @@ class FeatureOctree(nn.Module):
         self._desc_cache = {}
         self._hier_idx = []
         self._last_coord = None
+
+    @staticmethod
+    def _refresh_sorted(st):
+        """The sorted search arrays of the torch path, rebuilt from the authoritative per-row / per-node arrays when the
+        CUDA build path (which does not maintain them) grew the level."""
+        if st.node_keys_sorted.numel() != st.node_keys.numel():
+            st.node_keys_sorted = torch.sort(st.node_keys).values
+        if st.corner_lex_sorted.numel() != st.corner_morton_by_row.numel():
+            lex = _lex_key(morton_to_points(st.corner_morton_by_row))
+            order = torch.argsort(lex)
+            st.corner_lex_sorted, st.corner_rows_sorted = lex[order], order
+
+    def _grow_features(self, cur: int, n_fresh: int, first: bool, incremental_on: bool, dev):
+        """New rows of a level: feature_std * randn with the reference's call shapes (model/feature_octree.py:139,153),
+        trash row re-appended last."""
+        fts = self.feature_std * torch.randn(n_fresh + 1, self.feature_dim, device=dev)
+        fts[-1] = 0.0
+        if first:
+            self.hier_features.append(nn.Parameter(fts))
+            if incremental_on:
+                self.importance_weight.append(torch.zeros(n_fresh + 1, self.feature_dim, device=dev))
+                self.features_last_frame.append(fts.clone())
+        else:
+            self.hier_features[cur] = nn.Parameter(torch.cat((self.hier_features[cur].data[:-1], fts), 0))
+            if incremental_on:
+                new_w = torch.zeros(n_fresh + 1, self.feature_dim, device=dev)
+                self.importance_weight[cur] = torch.cat((self.importance_weight[cur][:-1], new_w), 0)
+                self.features_last_frame[cur] = self.hier_features[cur].data.clone()
+
+    def _update_cuda(self, pts, incremental_on):
+        """update() as kernels over the scan (csrc/shine_octree_build.cu): no unique/sort/searchsorted over the scan, one
+        radix sort over the NEW corners only; two small count read-backs size the tables and the new feature rows."""
+        lib = _abi.lib()
+        dev = pts.device
+        st_ptr = _abi.stream_ptr(dev)
+        n = pts.shape[0]
+        if n == 0:
+            return
+        L = self.featured_level_num
+        levels = list(range(self.free_level_num, self.max_level + 1))         # coarse -> fine, like hier_features
+        counts = torch.zeros(2 * L + 1, dtype=torch.int32, device=dev)
+        plan = _abi.ShineBuild()
+        plan.num_levels, plan.max_level = L, self.max_level
+        plan.new_node_count = counts.data_ptr()
+        plan.new_corner_count = counts.data_ptr() + 4 * L
+        plan.new_corner_total = counts.data_ptr() + 8 * L
+        set_cap = _next_pow2(2 * n)
+        node_sets = torch.full((L, set_cap), -1, dtype=torch.int64, device=dev)
+        new_keys = torch.empty(L, n, dtype=torch.int64, device=dev)
+        for l, lvl in enumerate(levels):
+            st = self._levels[lvl]
+            self._ensure_level_tables(st, lvl)
+            b = plan.lv[l]
+            b.level, b.nodes_before, b.rows_before = lvl, int(st.node_keys.numel()), int(st.corner_morton_by_row.numel())
+            b.node_slots = st.hash.data_ptr() if st.hash is not None else None
+            b.node_capacity = st.hash_capacity
+            b.frame_node_set, b.frame_node_set_capacity = node_sets[l].data_ptr(), set_cap
+            b.new_node_keys = new_keys[l].data_ptr()
+        _abi.check(lib.shine_octree_frame_nodes(C.byref(plan), _abi.ptr(pts), n, st_ptr), "shine_octree_frame_nodes")
+        c_nodes = counts[:L].tolist()                                          # read-back 1
+        if sum(c_nodes) == 0:
+            return
+        keep = []       # scratch referenced by the plan must outlive the launches
+        for l, lvl in enumerate(levels):
+            st = self._levels[lvl]
+            b = plan.lv[l]
+            self._reserve_node_table(st, lvl, b.nodes_before + c_nodes[l])
+            self._reserve_corner_table(st, b.rows_before + 8 * c_nodes[l])
+            b.node_slots, b.node_capacity = st.hash.data_ptr(), st.hash_capacity
+            b.corner_slots, b.corner_capacity = st.corner_hash.data_ptr(), st.corner_hash_capacity
+            cap = _next_pow2(16 * max(c_nodes[l], 1))
+            cs = torch.full((cap,), -1, dtype=torch.int64, device=dev)
+            ids = torch.empty(max(c_nodes[l], 1), 8, dtype=torch.int32, device=dev)
+            b.frame_corner_set, b.frame_corner_set_capacity = cs.data_ptr(), cap
+            b.node_ids_out = ids.data_ptr()
+            keep.append((cs, ids))
+        corner_keys = torch.empty(8 * sum(c_nodes), dtype=torch.int64, device=dev)
+        plan.new_corner_keys = corner_keys.data_ptr()
+        _abi.check(lib.shine_octree_frame_corners(C.byref(plan), max(c_nodes), st_ptr), "shine_octree_frame_corners")
+        c_corners = counts[L:].tolist()                                        # read-back 2
+        total = c_corners[-1]
+        sorted_keys = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
+        if total:
+            nbytes = int(lib.shine_octree_sort_scratch_bytes(total))
+            scratch = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+            _abi.check(lib.shine_octree_sort_corners(_abi.ptr(corner_keys), _abi.ptr(sorted_keys), total, _abi.ptr(scratch),
+                                                     nbytes, st_ptr), "shine_octree_sort_corners")
+        mortons = []
+        for l in range(L):
+            m = torch.empty(max(c_corners[l], 1), dtype=torch.int64, device=dev)
+            plan.lv[l].corner_morton_out = m.data_ptr()
+            mortons.append(m)
+        if total:
+            _abi.check(lib.shine_octree_assign_rows(C.byref(plan), _abi.ptr(sorted_keys), total, st_ptr),
+                       "shine_octree_assign_rows")
+        overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        _abi.check(lib.shine_octree_fill_nodes(C.byref(plan), max(c_nodes), _abi.ptr(overflow), st_ptr),
+                   "shine_octree_fill_nodes")
+        for l, lvl in enumerate(levels):          # ascending levels: the reference's randn call order (:139,153)
+            if c_nodes[l] == 0:
+                continue
+            st = self._levels[lvl]
+            first = st.corner_morton_by_row.numel() == 0 and len(self.hier_features) <= l
+            self._grow_features(l, c_corners[l], first, incremental_on, dev)
+            st.corner_morton_by_row = torch.cat((st.corner_morton_by_row, mortons[l][:c_corners[l]]))
+            st.node_keys = torch.cat((st.node_keys, new_keys[l, :c_nodes[l]]))
+            st.node_ids = torch.cat((st.node_ids, keep[l][1][:c_nodes[l]]))
+            st.hash_count = int(st.node_keys.numel())
+            st.corner_hash_count = int(st.corner_morton_by_row.numel())
+        if int(overflow.item()):
+            raise _abi.ShineB200Error("node table overflow while growing the octree")
+        self._dict_cache = None
+        self._desc_cache = {}
+        self._hier_idx = []
+        self._last_coord = None
+
+    def _ensure_level_tables(self, st, lvl):
+        """Device tables of a level that lost them (unpickled / moved): rebuild from the authoritative arrays."""
+        if st.node_keys.numel() and (st.hash is None or st.hash_count != st.node_keys.numel()):
+            self._ensure_hash()
+        if st.corner_morton_by_row.numel() and (st.corner_hash is None or
+                                                st.corner_hash_count != st.corner_morton_by_row.numel()):
+            st.corner_hash = None
+            self._reserve_corner_table(st, int(st.corner_morton_by_row.numel()))
+
+    def _reserve_node_table(self, st, lvl, n_total):
+        """Room for n_total nodes at the usual load factor; growing re-inserts the existing nodes."""
+        spn = max(1, int(self._HASH_SLOTS_PER_NODE))
+        if st.hash is not None and spn * n_total <= 2 * st.hash_capacity and n_total + 1 <= st.hash_capacity:
+            return
+        dev = st.node_keys.device
+        st.hash_capacity = _next_pow2(max(spn * max(n_total, 1), n_total + 1))
+        st.hash = torch.full((st.hash_capacity * _abi.HASH_SLOT_BYTES,), 0xFF, dtype=torch.uint8, device=dev)
+        n_old = int(st.node_keys.numel())
+        if n_old:
+            overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+            _abi.check(_abi.lib().shine_hash_insert(_abi.ptr(st.hash), st.hash_capacity, _abi.ptr(st.node_keys.contiguous()),
+                                                    _abi.ptr(st.node_ids.contiguous()), n_old, 0, _abi.ptr(overflow),
+                                                    _abi.stream_ptr(dev)), "shine_hash_insert")
+        st.hash_count = n_old
+
+    def _reserve_corner_table(self, st, n_total):
+        if st.corner_hash is not None and 2 * n_total <= st.corner_hash_capacity:
+            return
+        dev = st.node_keys.device
+        st.corner_hash_capacity = _next_pow2(4 * max(n_total, 1))
+        st.corner_hash = torch.full((st.corner_hash_capacity * 2,), -1, dtype=torch.int64, device=dev)
+        rows = int(st.corner_morton_by_row.numel())
+        if rows:
+            _abi.check(_abi.lib().shine_octree_corner_rehash(_abi.ptr(st.corner_hash), st.corner_hash_capacity,
+                                                             _abi.ptr(st.corner_morton_by_row.contiguous()), rows,
+                                                             _abi.stream_ptr(dev)), "shine_octree_corner_rehash")
+        st.corner_hash_count = rows
 
     def interpolat(self, x, level, polynomial_on=True):
         """The 8 blend weights as a tensor (reference :172-196) — kept for API parity; the kernels compute

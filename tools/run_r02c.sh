@@ -1,0 +1,11 @@
+set -x
+cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+timeout 900 python bench.py --steps 20 --warmup 5 2>gpurun_out/bench_r02c.err | tee gpurun_out/bench_r02c.json
+tail -3 gpurun_out/bench_r02c.err
+# launch list of the timed steps (share of the step per kernel)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-hbm-leg --cuda-profiler > gpurun_out/ncu_launch.log 2>&1
+# full capture: C2 training kernel, then the HBM-bound leg's
+timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:sdf_fused_kernel -c 1 -o gpurun_out/r02_step_c2 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-hbm-leg --cuda-profiler > gpurun_out/ncu_c2.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:sdf_fused_kernel --launch-skip 2 -c 1 -o gpurun_out/r02_step_hbm python bench.py --hbm-only --steps 5 > gpurun_out/ncu_hbm.log 2>&1
+ls -la gpurun_out | tail -8
