@@ -42,8 +42,9 @@ extern "C" {
 #define SHINE_FLAG_REDUCTION_SUM 1u   /* loss_reduction == "sum" (shine_incre.py:77-78); default mean   */
 #define SHINE_FLAG_WEIGHTED 2u        /* loss_weight_on (utils/loss.py:18-19): per-sample weight applied */
 #define SHINE_FLAG_TF32X1 4u          /* decoder contractions in plain TF32 (default: 3xTF32 ~ fp32)     */
-#define SHINE_FLAG_TCGEN05 8u         /* shine_sdf_infer only: tcgen05.mma / TMEM decoder (128 points per MMA,
-                                         thread-per-point gather and epilogues) instead of warp-level mma.sync */
+#define SHINE_FLAG_TCGEN05 8u         /* shine_sdf_infer / shine_sdf_bce_step: decoder on tcgen05.mma with TMEM accumulators
+                                         (128-point tiles, warp-specialised gather / epilogue warps) instead of
+                                         warp-level mma.sync                                                  */
 
 /* One featured level of the FeatureOctree (model/feature_octree.py:46-63). */
 typedef struct shine_level {

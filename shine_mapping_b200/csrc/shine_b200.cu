@@ -315,32 +315,6 @@ __device__ __forceinline__ void from_cfrag(const float (&c)[4], int odd, float (
 // (tcgen05.st / tcgen05.ld -> SASS STTM / LDTM) instead of pinning registers through the gather and MLP phases.
 // Warp w of the block owns TMEM lanes 32*(w&3).. and columns 64*(w>>2)..+55 of the block's 128-column allocation.
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                 : "=f"(v[0]),"=f"(v[1]),"=f"(v[2]),"=f"(v[3]),"=f"(v[4]),"=f"(v[5]),"=f"(v[6]),"=f"(v[7]),"=f"(v[8]),"=f"(v[9]),"=f"(v[10]),"=f"(v[11]),"=f"(v[12]),"=f"(v[13]),"=f"(v[14]),"=f"(v[15]),"=f"(v[16]),"=f"(v[17]),"=f"(v[18]),"=f"(v[19]),"=f"(v[20]),"=f"(v[21]),"=f"(v[22]),"=f"(v[23]),"=f"(v[24]),"=f"(v[25]),"=f"(v[26]),"=f"(v[27]),"=f"(v[28]),"=f"(v[29]),"=f"(v[30]),"=f"(v[31]) : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=f"(v[0]),"=f"(v[1]),"=f"(v[2]),"=f"(v[3]),"=f"(v[4]),"=f"(v[5]),"=f"(v[6]),"=f"(v[7]),"=f"(v[8]),"=f"(v[9]),"=f"(v[10]),"=f"(v[11]),"=f"(v[12]),"=f"(v[13]),"=f"(v[14]),"=f"(v[15]) : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(v[0]),"=f"(v[1]),"=f"(v[2]),"=f"(v[3]),"=f"(v[4]),"=f"(v[5]),"=f"(v[6]),"=f"(v[7]) : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
-                 :: "r"(taddr), "f"(v[0]),"f"(v[1]),"f"(v[2]),"f"(v[3]),"f"(v[4]),"f"(v[5]),"f"(v[6]),"f"(v[7]),"f"(v[8]),"f"(v[9]),"f"(v[10]),"f"(v[11]),"f"(v[12]),"f"(v[13]),"f"(v[14]),"f"(v[15]),"f"(v[16]),"f"(v[17]),"f"(v[18]),"f"(v[19]),"f"(v[20]),"f"(v[21]),"f"(v[22]),"f"(v[23]),"f"(v[24]),"f"(v[25]),"f"(v[26]),"f"(v[27]),"f"(v[28]),"f"(v[29]),"f"(v[30]),"f"(v[31]) : "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-                 :: "r"(taddr), "f"(v[0]),"f"(v[1]),"f"(v[2]),"f"(v[3]),"f"(v[4]),"f"(v[5]),"f"(v[6]),"f"(v[7]),"f"(v[8]),"f"(v[9]),"f"(v[10]),"f"(v[11]),"f"(v[12]),"f"(v[13]),"f"(v[14]),"f"(v[15]) : "memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 :: "r"(taddr), "f"(v[0]),"f"(v[1]),"f"(v[2]),"f"(v[3]),"f"(v[4]),"f"(v[5]),"f"(v[6]),"f"(v[7]) : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // register view: dW2[2][4][4] (cols 0..31), dW1[2][4] (32..39), db2[4][2] (40..47), db1[4][2] (48..55), dw3[4][2] (56..63)
 #define SHINE_ACC_DECL float dW2[2][4][4], dW1[2][4], db2p[4][2], db1p[4][2], dw3p[4][2]
 #define SHINE_ACC_LOAD(ta)                                                                             \
@@ -360,23 +334,7 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 
 constexpr int kGatherGroup = SHINE_GATHER_GROUP;
 
-struct StepParams {
-    shine_octree oct;
-    shine_decoder dec;
-    const float* coord;
-    const float* label;
-    const float* weight;     // nullable (ignored unless weighted)
-    const float* d_loss;     // nullable device scalar
-    float* pred;             // nullable
-    float* loss;             // nullable, accumulated
-    uint8_t* mask;           // nullable (infer only)
-    int64_t n;
-    int32_t num_tiles;
-    int32_t mask_level;
-    float sigma;
-    float loss_scale;
-    int32_t weighted;
-};
+using shine_internal::StepParams;
 
 // shared-memory plan (floats).  Weight matrices are pre-split into tf32 hi / lo words.
 struct SmemPlan {
@@ -1047,25 +1005,6 @@ struct TcPlan {                                   // byte offsets in dynamic sha
     static constexpr int BYTES = BAR + 16;
 };
 
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);      // version 1 (Blackwell), SWIZZLE_NONE
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
-        ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (int spin = 0; !done; ++spin) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (spin > (1 << 22)) __trap();   // never hang the GPU on a protocol bug
-    }
-}
-
 template <int LMAX>
 __global__ void __launch_bounds__(128, 5) sdf_infer_tc_kernel(const __grid_constant__ StepParams P) {
     extern __shared__ __align__(128) unsigned char tsm[];
@@ -1665,6 +1604,10 @@ int shine_sdf_bce_step(const shine_octree* oct, const shine_decoder* dec, const 
     DeviceGuard guard(oct->lv[0].features);
     P.label = label; P.weight = weight; P.weighted = (flags & SHINE_FLAG_WEIGHTED) ? 1 : 0;
     P.sigma = sigma; P.loss_scale = loss_scale; P.d_loss = d_loss; P.pred = out_pred; P.loss = out_loss;
+    if ((flags & SHINE_FLAG_TCGEN05) && !(flags & SHINE_FLAG_TF32X1)) {
+        rc = shine_internal::launch_train_tc(P, dec_grad, (cudaStream_t)stream);
+        if (rc != SHINE_ERR_UNSUPPORTED) return rc;      // > 4 levels: the mma.sync kernel below handles it
+    }
     return dec_grad ? launch_fused<true, true>(P, flags, (cudaStream_t)stream)
                     : launch_fused<true, false>(P, flags, (cudaStream_t)stream);
 }

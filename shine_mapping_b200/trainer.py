@@ -28,7 +28,7 @@ def _align4(n: int) -> int:
 
 class SdfTrainer:
     def __init__(self, config: SHINEConfig, octree: FeatureOctree, decoder: Decoder, process_group=None,
-                 tf32x1: bool = False, shard_mode: str = "replicated", boundary=None, comm=None):
+                 tf32x1: bool = False, shard_mode: str = "replicated", boundary=None, comm=None, tcgen05=None):
         """shard_mode (multi-GPU, see dist.py / partition.py): "replicated" = every rank holds the whole table and a
         slice of the point batch -> all-reduce the whole flat gradient; "spatial" = every rank owns a Morton-prefix
         range of ONE map and the samples inside it (BASELINE config 5) -> ONE all-reduce over
@@ -43,6 +43,8 @@ class SdfTrainer:
         self.use_replicas = os.environ.get("SHINE_FUSED_REPLICAS", "1") != "0"
         self.group = process_group
         self.tf32x1 = tf32x1
+        # decoder of the fused step on tcgen05.mma / TMEM (csrc/shine_train_tc.cu); None = the library default
+        self.tcgen05 = (os.environ.get("SHINE_TRAIN_TCGEN05", "0") == "1") if tcgen05 is None else bool(tcgen05)
         self.lr = config.lr
         self.step_count = 0
         self._sig = None
@@ -120,7 +122,8 @@ class SdfTrainer:
         if weighted and weight is None:
             raise ValueError("loss_weight_on needs the per-sample weight tensor")
         flags = (_abi.FLAG_REDUCTION_SUM if cfg.loss_reduction == "sum" else 0) | \
-                (_abi.FLAG_WEIGHTED if weighted else 0) | (_abi.FLAG_TF32X1 if self.tf32x1 else 0)
+                (_abi.FLAG_WEIGHTED if weighted else 0) | (_abi.FLAG_TF32X1 if self.tf32x1 else 0) | \
+                (_abi.FLAG_TCGEN05 if self.tcgen05 else 0)
         scale = 1.0 if cfg.loss_reduction == "sum" else 1.0 / float(n_norm if n_norm else n)
         od = self.octree._descriptor(None, self.table_grads, n_points=n if self.use_replicas else 0)
         dd = self.decoder.c_descriptor(self.dec_grads if self._dec_trainable else None)

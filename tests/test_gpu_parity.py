@@ -392,3 +392,45 @@ def test_abi_rejects_bad_arguments():
     d.num_levels = 0
     assert lib.shine_query_fwd(C.byref(d), None, 4, None, None) == -1
     assert b"invalid" in lib.shine_error_string(-1)
+
+
+# ---- the tcgen05 / TMEM training kernel (csrc/shine_train_tc.cu) ---------------------------------------------------------
+
+def _trainer_step(case, tcgen05, freeze=False):
+    from shine_mapping_b200 import SdfTrainer
+    cfg, octree, dec = build_cuda_models(case, DEV, freeze_decoder=freeze)
+    coord = torch.from_numpy(case["coord"]).to(DEV); label = torch.from_numpy(case["label"]).to(DEV)
+    weight = torch.from_numpy(case["weight"]).to(DEV)
+    tr = SdfTrainer(cfg, octree, dec, tcgen05=tcgen05)
+    tr.zero_grad()
+    pred = torch.empty(coord.shape[0], device=DEV)
+    loss = tr.forward_backward(coord, label, weight, pred_out=pred)
+    torch.cuda.synchronize()
+    return {
+        "indices": [t.cpu().numpy() for t in octree.get_indices(coord)],
+        "feature": octree.query_feature(coord).detach().cpu().numpy(),
+        "pred": pred.cpu().numpy(), "loss": float(loss),
+        "table_grads": [g.detach().cpu().numpy().copy() for g in tr.table_grads],
+        "dec_grads": {} if freeze else {k: g.detach().cpu().numpy().copy() for k, g in zip(DEC_KEYS, tr.dec_grads)},
+    }
+
+
+@pytest.mark.parametrize("levels,poly,weighted,reduction,n_batch", [
+    (4, True, False, "mean", 3000), (2, True, False, "mean", 100), (3, False, True, "sum", 5000),
+    (4, True, True, "mean", 60000),          # > 148 tiles of 128 points: several rounds per CTA, both gather groups busy
+    (1, True, False, "mean", 0),             # 16 stragglers only: one partial tile
+])
+def test_tcgen05_train_step_matches_oracle(levels, poly, weighted, reduction, n_batch):
+    """SHINE_FLAG_TCGEN05 on shine_sdf_bce_step: decoder forward / dgrad / wgrad as tcgen05.mma on 128-point tiles
+    (operands in shared memory, accumulators in TMEM), same tolerances as the mma.sync kernel."""
+    case = make_case(n_points=2500, n_batch=n_batch, feat_levels=levels, seed=40 + levels, poly=poly, weighted=weighted,
+                     reduction=reduction, n_frames=2 if n_batch > 10000 else 1)
+    print(compare_step(_trainer_step(case, True), run_oracle_step(case)))
+
+
+def test_tcgen05_train_step_frozen_decoder():
+    case = make_case(n_points=2500, n_batch=4000, feat_levels=4, seed=47)
+    got = _trainer_step(case, True, freeze=True)
+    want = run_oracle_step(case)
+    want["dec_grads"] = {}
+    print(compare_step(got, want))
