@@ -73,6 +73,7 @@ __global__ void hash_insert_kernel(HashSlot* __restrict__ slots, uint32_t mask, 
                 slots[h].ids0[c] = corner_ids[i * 8 + 2 * c];
                 slots[h].ids1[c] = corner_ids[i * 8 + 2 * c + 1];
             }
+            note_displacement(slots, h0, it);
             return;
         }
     }
@@ -590,7 +591,8 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         {
             constexpr int LH = LMAX / 2;
             const unsigned long long key0 = valid ? morton_of(x, y, z, P.oct.lv[0].level) : 0ull;
-            unsigned long long kq[LH], kf[LH];
+            unsigned long long kq[LH];
+            uint4 kf[LH];          // home slot: {key lo, key hi, node, maxdisp}
             int mine[LH];
 #pragma unroll
             for (int j = 0; j < LH; ++j) {
@@ -601,19 +603,23 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                     const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
                     kq[j] = consecutive ? (key0 >> (3 * i)) : morton_of(x, y, z, lv.level);
                     mine[j] = (int)(hash_key(kq[j]) & (lv.hash_capacity - 1));
-                    kf[j] = __ldg(&slots[mine[j]].key);
+                    kf[j] = __ldg(reinterpret_cast<const uint4*>(slots + mine[j]));
                 }
             }
 #pragma unroll
             for (int j = 0; j < LH; ++j) {
                 const int i = 2 * j + half;
-                if (i < L && valid && kf[j] != kq[j]) {
-                    if (kf[j] == kEmptyKey) {
-                        mine[j] = -1;
-                    } else {   // first-probe collision (rare at load factor <= 0.5): walk on
-                        const shine_level& lv = P.oct.lv[i];
-                        mine[j] = probe_slot_from(reinterpret_cast<const HashSlot*>(lv.hash_slots),
-                                                  lv.hash_capacity - 1, kq[j], (uint32_t)mine[j], 1u);
+                if (i < L && valid) {
+                    const unsigned long long k0 = ((unsigned long long)kf[j].y << 32) | kf[j].x;
+                    if (k0 != kq[j]) {
+                        // not in its home slot: a miss unless the home slot says one of its keys was displaced (rare)
+                        if (k0 == kEmptyKey || (int)kf[j].w <= 0) {
+                            mine[j] = -1;
+                        } else {
+                            const shine_level& lv = P.oct.lv[i];
+                            mine[j] = probe_slot_from(reinterpret_cast<const HashSlot*>(lv.hash_slots),
+                                                      lv.hash_capacity - 1, kq[j], (uint32_t)mine[j], (int)kf[j].w);
+                        }
                     }
                 }
             }
@@ -1398,7 +1404,7 @@ int fill_params(StepParams& P, const shine_octree* oct, const shine_decoder* dec
     P.oct = *oct; P.dec = *dec; P.coord = coord; P.n = n;
     P.num_tiles = (int32_t)((n + kTile - 1) / kTile);
     P.label = nullptr; P.weight = nullptr; P.d_loss = nullptr; P.pred = nullptr; P.loss = nullptr; P.mask = nullptr;
-    P.mask_level = 0; P.sigma = 1.f; P.loss_scale = 1.f; P.weighted = 0;
+    P.mask_level = 0; P.sigma = 1.f; P.loss_scale = 1.f; P.weighted = 0; P.debug_dx = nullptr;
     return SHINE_OK;
 }
 

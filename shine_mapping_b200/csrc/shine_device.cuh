@@ -28,6 +28,7 @@ struct StepParams {
     float sigma;
     float loss_scale;
     int32_t weighted;
+    float* debug_dx;         // development aid: dL/dfeature rows [n, 8] of the tcgen05 training kernel (NULL in normal use)
 };
 
 // shine_train_tc.cu: the warp-specialised tcgen05 training kernel (SHINE_FLAG_TCGEN05 on shine_sdf_bce_step)
@@ -55,10 +56,13 @@ constexpr unsigned kFull = 0xFFFFFFFFu;
 struct __align__(64) HashSlot {
     unsigned long long key;   // Morton code of the voxel, kEmptyKey when free
     int32_t node;             // insertion ordinal (diagnostics)
-    int32_t pad0;
+    int32_t maxdisp;          // as HOME slot: largest probe index of any key whose probe sequence starts here (<= 0: none
+                              // was displaced) — a lookup that does not find its key in its home slot stops right there
+                              // unless this says that some key of this home lives further along
     int32_t ids0[4];          // rows of corners c0 c2 c4 c6 (z bit 0)
     unsigned long long key2;  // copy of key (written after the slot is claimed through `key`)
-    int32_t pad1[2];
+    int32_t pad1;
+    int32_t maxdisp2;         // copy of maxdisp for the lane that reads sector 1
     int32_t ids1[4];          // rows of corners c1 c3 c5 c7 (z bit 1)
 };
 static_assert(sizeof(HashSlot) == SHINE_HASH_SLOT_BYTES, "slot must be 64 bytes");
@@ -179,12 +183,17 @@ __host__ __device__ __forceinline__ uint32_t probe_pos(uint32_t h0, uint32_t k, 
 }
 
 // nodes_lookup_tables[level].get(morton, [-1]*8)  (model/feature_octree.py:205-209) as an open-addressing probe.
-// Returns the slot index or -1.
+// Returns the slot index or -1.  The home slot's `maxdisp` bounds the walk: most misses end at the first probe.
 __device__ __forceinline__ int probe_slot(const HashSlot* __restrict__ slots, uint32_t mask, unsigned long long key) {
     const uint32_t h0 = hash_key(key) & mask;
+    const uint4 first = __ldg(reinterpret_cast<const uint4*>(slots + h0));        // {key lo, key hi, node, maxdisp}
+    const unsigned long long k0 = ((unsigned long long)first.y << 32) | first.x;
+    if (k0 == key) return (int)h0;
+    const int last = (int)first.w;
+    if (k0 == kEmptyKey || last <= 0) return -1;
 #pragma unroll 1
-    for (uint32_t n = 0; n <= mask; ++n) {
-        const uint32_t h = probe_pos(h0, n, mask);
+    for (int n = 1; n <= last; ++n) {
+        const uint32_t h = probe_pos(h0, (uint32_t)n, mask);
         const unsigned long long k = __ldg(&slots[h].key);
         if (k == key) return (int)h;
         if (k == kEmptyKey) return -1;
@@ -192,21 +201,26 @@ __device__ __forceinline__ int probe_slot(const HashSlot* __restrict__ slots, ui
     return -1;
 }
 
-// continuation of a walk whose probes 0 .. first-1 have already been looked at (and were neither the key nor empty)
+// continuation of a walk whose home slot h0 was neither the key nor empty: probes 1 .. last
 __device__ __noinline__ int probe_slot_from(const HashSlot* __restrict__ slots, uint32_t mask, unsigned long long key,
-                                            uint32_t h0, uint32_t first) {
+                                            uint32_t h0, int last) {
 #pragma unroll 1
-    for (uint32_t n = first; n <= mask; ++n) {
-        const uint32_t h = probe_pos(h0, n, mask);
+    for (int n = 1; n <= last; ++n) {
+        const uint32_t h = probe_pos(h0, (uint32_t)n, mask);
         const unsigned long long k = __ldg(&slots[h].key);
         if (k == key) return (int)h;
         if (k == kEmptyKey) return -1;
     }
     return -1;
+}
+
+// insertion side: record that a key of home h0 went to probe index `it`
+__device__ __forceinline__ void note_displacement(HashSlot* slots, uint32_t h0, uint32_t it) {
+    if (it > 0) { atomicMax(&slots[h0].maxdisp, (int32_t)it); atomicMax(&slots[h0].maxdisp2, (int32_t)it); }
 }
 
 // one 32-byte sector of a slot: {key (2 words), 2 words of padding / ordinal, 4 corner rows}
-struct SlotSector { unsigned long long key; int32_t ids[4]; };
+struct SlotSector { unsigned long long key; int32_t maxdisp; int32_t ids[4]; };
 __device__ __forceinline__ SlotSector ldg_sector(const HashSlot* slots, uint32_t s, int half) {
     uint32_t w[8];
     const void* p = reinterpret_cast<const char*>(slots + s) + 32 * half;
@@ -215,6 +229,7 @@ __device__ __forceinline__ SlotSector ldg_sector(const HashSlot* slots, uint32_t
                  : "l"(p));
     SlotSector r;
     r.key = ((unsigned long long)w[1] << 32) | w[0];
+    r.maxdisp = (int32_t)w[3];
     r.ids[0] = (int32_t)w[4]; r.ids[1] = (int32_t)w[5]; r.ids[2] = (int32_t)w[6]; r.ids[3] = (int32_t)w[7];
     return r;
 }
@@ -225,7 +240,7 @@ __device__ __forceinline__ bool resolve_sector(const HashSlot* slots, uint32_t m
                                                SlotSector& sec) {
     if (sec.key == key) return true;
     int s = -1;
-    if (sec.key != kEmptyKey) s = probe_slot_from(slots, mask, key, hash_key(key) & mask, 1u);
+    if (sec.key != kEmptyKey && sec.maxdisp > 0) s = probe_slot_from(slots, mask, key, hash_key(key) & mask, sec.maxdisp);
     if (s >= 0) {
         const int4 v = __ldg(reinterpret_cast<const int4*>(slot_ids(slots, s, half)));
         sec.ids[0] = v.x; sec.ids[1] = v.y; sec.ids[2] = v.z; sec.ids[3] = v.w;

@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(256) fill_nodes_kernel(const __grid_constant__
                 slots[h].key2 = key;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) { slots[h].ids0[c] = ids[2 * c]; slots[h].ids1[c] = ids[2 * c + 1]; }
+                note_displacement(slots, h0, it);
                 stored = true;
             }
         }
