@@ -61,7 +61,7 @@ def build_workload(device, rank, world, n_azimuth):
 SCAN_SPACING_M = 25.0    # multi-GPU map: one scan per GPU, 25 m apart along the street (pc_radius 50 m: they overlap)
 
 
-def build_partitioned_workload(device, rank, world, n_azimuth, n_frames=None):
+def build_partitioned_workload(device, rank, world, n_azimuth, n_frames=None, exchange="nccl"):
     """N > 1: ONE map of `world` overlapping scans, partitioned by Morton prefix at the coarsest featured level into
     `world` balanced ranges (partition.py).  Every rank generates the same global pool (seeded), keeps the samples of its
     range, grows its own octree from them; corner rows on the faces between ranges are duplicated and exchanged every
@@ -93,9 +93,14 @@ def build_partitioned_workload(device, rank, world, n_azimuth, n_frames=None):
                                   partition.decoder_segment_floats(decoder)).to(device)
     if comm is not None:
         plan.unify_values(list(octree.hier_features), comm.all_reduce)
+    p2p = None
+    if world > 1 and exchange == "p2p":
+        p2p = sdist.P2PExchange(rank, world, torch.device(device), plan.total_floats)
     info = {"global_pool_samples": global_pool, "scans": n_frames, "scan_spacing_m": SCAN_SPACING_M,
-            "boundary_rows": [int(c) for c in plan.counts], "exchange_floats": int(plan.total_floats)}
-    return cfg, octree, decoder, pool, plan, comm, info
+            "boundary_rows": [int(c) for c in plan.counts], "exchange_floats": int(plan.total_floats),
+            "exchange": "one NVLink peer-memory kernel (pack + publish + wait + reduce in place), IPC buffers" if p2p else
+                        "shine_boundary_pack -> ncclAllReduce through the C ABI -> shine_boundary_unpack"}
+    return cfg, octree, decoder, pool, plan, comm, p2p, info
 
 
 def shared_config(cfg, n_azimuth, pool_len, n, world, rows):
@@ -437,10 +442,11 @@ def run_ours(args):
     numa = sdist.pin_to_gpu_numa_node(local) if world > 1 else {"numa_node": sdist.gpu_numa_node(local), "cpus": None}
     part_info = None
     if world > 1:
-        cfg, octree, decoder, pool, plan, comm, part_info = build_partitioned_workload(str(dev), rank, world, args.n_azimuth)
+        cfg, octree, decoder, pool, plan, comm, p2p, part_info = build_partitioned_workload(
+            str(dev), rank, world, args.n_azimuth, exchange=args.exchange)
         # weak scaling: every GPU steps as many points as the single GPU does (one scan's worth), drawn from ITS range
         n = (args.points if args.points > 0 else C2_POINTS_PER_STEP) if args.global_points <= 0 else args.global_points // world
-        trainer = SdfTrainer(cfg, octree, decoder, shard_mode="spatial", boundary=plan, comm=comm)
+        trainer = SdfTrainer(cfg, octree, decoder, shard_mode="spatial", boundary=plan, comm=comm, p2p=p2p)
     else:
         cfg, octree, decoder, pool = build_workload(str(dev), rank, world, args.n_azimuth)
         n = len(pool) if args.points <= 0 else args.points
@@ -544,8 +550,8 @@ def run_ours(args):
         "config": shared_config(cfg, args.n_azimuth, len(pool), n, world, rows),
         "impl_notes": {"decoder_math": "3xTF32 mma.sync (fp32-grade)",
                        "parallelism": "single GPU" if world == 1 else
-                       f"one map, Morton-prefix ranges x{world}; ONE NCCL all-reduce per step over [decoder grads | "
-                       "gradients of corner rows shared between ranges] through the C ABI",
+                       f"one map, Morton-prefix ranges x{world}; ONE exchange per step over [decoder grads | "
+                       "gradients of corner rows shared between ranges] (see partition.exchange)",
                        "partition": part_info,
                        "l2": "flushed between timed steps (256 MiB write, not timed)",
                        "timed_step": "grad memset + fused fwd+loss+bwd kernel + replica fold (+ all-reduce when N>1)"},
@@ -605,6 +611,8 @@ def main():
                          "cpu_baseline / parity legs of our arm default to 100000")
     ap.add_argument("--hbm-frames", type=int, default=100, help="frames of the HBM-bound leg's map")
     ap.add_argument("--hbm-points", type=int, default=1 << 20, help="points per step of the HBM-bound leg")
+    ap.add_argument("--exchange", default=os.environ.get("SHINE_EXCHANGE", "nccl"), choices=["nccl", "p2p"],
+                    help="N>1: the step's exchange — NCCL all-reduce through the C ABI, or the one-kernel NVLink peer-memory path")
     ap.add_argument("--no-hbm-leg", action="store_true")
     ap.add_argument("--hbm-only", action="store_true", help="run only the HBM-bound leg and print its object (ncu target)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

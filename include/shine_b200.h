@@ -288,6 +288,21 @@ int shine_nccl_comm_destroy(void* comm);
 int shine_allreduce_decoder_grads(void* comm, float* buf, int64_t count, void* stream);
 const char* shine_comm_last_error(void);
 
+/* The same exchange as ONE kernel over NVLink peer memory (no NCCL): pack own [decoder | boundary rows] into an
+ * IPC-shared buffer, publish a step flag into every peer's buffer, wait for the peers' flags, sum all ranks' buffers
+ * in fixed rank order straight over NVLink, in place into dec_grads / the plan's table rows.  One process per GPU:
+ * create (returns the 64-byte cudaIpcMemHandle_t of this rank's buffer) -> the caller all-gathers the handles ->
+ * connect -> exchange every step (all ranks, same order).  plan offsets are relative to the exchange buffer whose first
+ * dec_floats floats are the decoder segment, exactly as for shine_boundary_pack.  A peer that never shows up is a
+ * counted timeout (shine_p2p_timeouts), not a hang. */
+typedef struct shine_p2p shine_p2p;
+int shine_p2p_create(int32_t nranks, int32_t rank, int32_t device, int64_t max_floats, void* out_handle64, shine_p2p** out);
+int shine_p2p_connect(shine_p2p* ctx, const void* handles /* nranks x 64 B, rank order */);
+int shine_p2p_exchange(shine_p2p* ctx, float* dec_grads, int64_t dec_floats, const shine_boundary* plan,
+                       int32_t num_levels, int32_t feature_dim, void* stream);
+int shine_p2p_timeouts(shine_p2p* ctx, int32_t* out_count);
+int shine_p2p_destroy(shine_p2p* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -122,6 +122,11 @@ SYMBOLS = {
     "shine_nccl_comm_destroy": (C.c_int, [_vp]),
     "shine_allreduce_decoder_grads": (C.c_int, [_vp, _vp, _i64, _vp]),
     "shine_comm_last_error": (C.c_char_p, []),
+    "shine_p2p_create": (C.c_int, [_i32, _i32, _i32, _i64, _vp, C.POINTER(C.c_void_p)]),
+    "shine_p2p_connect": (C.c_int, [_vp, _vp]),
+    "shine_p2p_exchange": (C.c_int, [_vp, _vp, _i64, C.POINTER(ShineBoundary), _i32, _i32, _vp]),
+    "shine_p2p_timeouts": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
+    "shine_p2p_destroy": (C.c_int, [_vp]),
     "shine_adam_step": (C.c_int, [C.POINTER(ShineAdamTensor), _i32, _f32, _f32, _f32, _i32, _i32, _vp]),
     "shine_adam_step_dev": (C.c_int, [C.POINTER(ShineAdamTensor), _i32, _f32, _f32, _f32, _vp, _i32, _vp]),
 }

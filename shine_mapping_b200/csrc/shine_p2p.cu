@@ -1,0 +1,223 @@
+// shine_p2p.cu — the step's multi-GPU exchange as ONE kernel over NVLink peer memory.
+//
+// What is exchanged every step: the 1 377 decoder gradients and the gradients of the corner rows that a spatial
+// partition duplicates on range faces — a few KB to a few hundred KB, i.e. latency-bound.  The NCCL route
+// (shine_boundary_pack -> ncclAllReduce -> shine_boundary_unpack) is three launches and ~20 us of collective latency; here
+// every rank runs one small kernel:
+//     1. pack      own decoder segment + own boundary rows -> own exchange buffer (parity = step & 1)
+//     2. publish   last block to finish: __threadfence_system, then store the step number into its flag slot in EVERY
+//                  peer's buffer (plain stores through the peers' IPC-mapped pointers)
+//     3. wait      until every peer's flag in the local buffer has reached the step number (bounded spin)
+//     4. reduce    out[i] = sum over ranks 0..n-1 (fixed order: bitwise identical on every rank) of the peers' buffers,
+//                  read straight over NVLink, written in place into the decoder gradients / the table-gradient rows
+// Double buffering by step parity replaces the trailing barrier: a rank can only overwrite parity p two steps later, and
+// it cannot get there before every peer has published the step in between, i.e. has finished reading parity p.
+// Buffers are cudaMalloc'ed here and shared with cudaIpc*MemHandle (one process per GPU).
+#include <string.h>
+
+#include "shine_device.cuh"
+
+struct shine_p2p {
+    int32_t nranks, rank, device;
+    int64_t max_floats;
+    unsigned char* local;              // [flags 4 KB | control 256 B | data 2 x max_floats x 4]
+    unsigned char* peer[16];           // IPC-mapped bases (peer[rank] == local)
+    bool opened[16];
+    uint32_t step;
+};
+
+namespace {
+
+constexpr int kFlagStride = 128;        // one line per publishing rank
+constexpr int kCtrlOff = 4096;          // {uint32 arrive; uint32 timeouts}
+constexpr int kDataOff = 4096 + 256;
+constexpr int kMaxRanks = 16;
+constexpr long long kSpinLimit = 1ll << 24;     // ~0.3 s of polling: a missing peer becomes an error flag, not a hang
+
+struct P2PParams {
+    unsigned char* peer[kMaxRanks];
+    int32_t nranks, rank;
+    uint32_t step;
+    int64_t max_floats, dec_floats;
+    float* dec;                         // decoder segment (in place)
+    shine_boundary plan;                // table-gradient rows shared with other ranks
+    int32_t num_levels, feature_dim;
+};
+
+__device__ __forceinline__ float* data_of(unsigned char* base, uint32_t step, int64_t max_floats) {
+    return reinterpret_cast<float*>(base + kDataOff) + (int64_t)(step & 1u) * max_floats;
+}
+// peers' buffers are read past L1 (they were written by another GPU)
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(512) p2p_exchange_kernel(const __grid_constant__ P2PParams P) {
+    unsigned char* mine_base = P.peer[P.rank];
+    float* mine = data_of(mine_base, P.step, P.max_floats);
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gs = (int64_t)gridDim.x * blockDim.x;
+    const int lp = P.feature_dim >> 2;
+
+    // 1. pack
+    for (int64_t i = gt; i < P.dec_floats / 4; i += gs)
+        reinterpret_cast<float4*>(mine)[i] = reinterpret_cast<const float4*>(P.dec)[i];
+    for (int l = 0; l < P.num_levels; ++l) {
+        const shine_boundary_level& b = P.plan.lv[l];
+        for (int64_t i = gt; i < (int64_t)b.count * lp; i += gs) {
+            const int r = (int)(i / lp), part = (int)(i % lp);
+            reinterpret_cast<float4*>(mine + b.offset + (int64_t)b.slots[r] * P.feature_dim)[part] =
+                reinterpret_cast<const float4*>(b.table + (int64_t)b.rows[r] * P.feature_dim)[part];
+        }
+    }
+    // 2. publish (last block)
+    volatile uint32_t* ctrl = reinterpret_cast<volatile uint32_t*>(mine_base + kCtrlOff);
+    __shared__ int is_last;
+    __threadfence_system();                 // every thread: its packed values are visible to the peers before the flag
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t prev = atomicAdd(const_cast<uint32_t*>(ctrl), 1u);
+        is_last = prev == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last) {
+        if (threadIdx.x == 0) ctrl[0] = 0u;                               // ready for the next launch
+        __threadfence_system();
+        if (threadIdx.x < P.nranks) {
+            volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(P.peer[threadIdx.x] + (size_t)P.rank * kFlagStride);
+            *flag = P.step;
+        }
+    }
+    // 3. wait for every rank's publication of this step
+    if (threadIdx.x < P.nranks) {
+        volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(mine_base + (size_t)threadIdx.x * kFlagStride);
+        long long spin = 0;
+        while ((int32_t)(*flag - P.step) < 0) {
+            if (++spin > kSpinLimit) { atomicAdd(const_cast<uint32_t*>(ctrl) + 1, 1u); break; }
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    // 4. reduce, fixed rank order, in place
+    for (int64_t i = gt; i < P.dec_floats / 4; i += gs) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < P.nranks; ++r) {
+            const float4 v = ld_peer_f4(data_of(P.peer[r], P.step, P.max_floats) + 4 * i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(P.dec)[i] = acc;
+    }
+    for (int l = 0; l < P.num_levels; ++l) {
+        const shine_boundary_level& b = P.plan.lv[l];
+        for (int64_t i = gt; i < (int64_t)b.count * lp; i += gs) {
+            const int row = (int)(i / lp), part = (int)(i % lp);
+            const int64_t off = b.offset + (int64_t)b.slots[row] * P.feature_dim;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int r = 0; r < P.nranks; ++r) {
+                const float4 v = ld_peer_f4(data_of(P.peer[r], P.step, P.max_floats) + off + 4 * part);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            reinterpret_cast<float4*>(b.table + (int64_t)b.rows[row] * P.feature_dim)[part] = acc;
+        }
+    }
+}
+
+// the slots a rank does not hold must read as zero on it: cleared once per parity and kept clean by construction (a rank
+// only ever writes the slots of its own rows, always the same ones)
+
+}  // namespace
+
+extern "C" {
+
+int shine_p2p_create(int32_t nranks, int32_t rank, int32_t device, int64_t max_floats, void* out_handle64, shine_p2p** out) {
+    if (nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks || max_floats < 4 || !out_handle64 || !out)
+        return SHINE_ERR_INVALID_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return (int)e;
+    shine_p2p* ctx = new shine_p2p();
+    ctx->nranks = nranks; ctx->rank = rank; ctx->device = device; ctx->step = 0;
+    ctx->max_floats = (max_floats + 3) & ~(int64_t)3;
+    for (int i = 0; i < kMaxRanks; ++i) { ctx->peer[i] = nullptr; ctx->opened[i] = false; }
+    const size_t bytes = (size_t)kDataOff + 2 * (size_t)ctx->max_floats * sizeof(float);
+    e = cudaMalloc(reinterpret_cast<void**>(&ctx->local), bytes);
+    if (e == cudaSuccess) e = cudaMemset(ctx->local, 0, bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, ctx->local);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (prev >= 0 && prev != device) cudaSetDevice(prev);
+    if (e != cudaSuccess) { if (ctx->local) cudaFree(ctx->local); delete ctx; return (int)e; }
+    memcpy(out_handle64, &h, sizeof(h));
+    ctx->peer[rank] = ctx->local;
+    *out = ctx;
+    return SHINE_OK;
+}
+
+int shine_p2p_connect(shine_p2p* ctx, const void* handles) {
+    if (!ctx || !handles) return SHINE_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->local);
+    for (int r = 0; r < ctx->nranks; ++r) {
+        if (r == ctx->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, reinterpret_cast<const unsigned char*>(handles) + (size_t)r * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return (int)e;
+        ctx->peer[r] = reinterpret_cast<unsigned char*>(p);
+        ctx->opened[r] = true;
+    }
+    return SHINE_OK;
+}
+
+int shine_p2p_exchange(shine_p2p* ctx, float* dec_grads, int64_t dec_floats, const shine_boundary* plan, int32_t num_levels,
+                       int32_t feature_dim, void* stream) {
+    if (!ctx || !dec_grads || dec_floats < 0 || (dec_floats & 3) || num_levels < 0 || num_levels > SHINE_MAX_LEVELS)
+        return SHINE_ERR_INVALID_ARG;
+    if (num_levels > 0 && (!plan || feature_dim < 4 || (feature_dim & 3))) return SHINE_ERR_INVALID_ARG;
+    P2PParams P;
+    int64_t most = dec_floats / 4, end = dec_floats;
+    for (int l = 0; l < num_levels; ++l) {
+        const shine_boundary_level& b = plan->lv[l];
+        if (b.count < 0 || (b.count > 0 && (!b.table || !b.rows || !b.slots)) || (b.offset & 3) || b.offset < dec_floats)
+            return SHINE_ERR_INVALID_ARG;
+        if ((int64_t)b.count * (feature_dim / 4) > most) most = (int64_t)b.count * (feature_dim / 4);
+        P.plan.lv[l] = b;
+    }
+    (void)end;
+    for (int r = 0; r < kMaxRanks; ++r) P.peer[r] = r < ctx->nranks ? ctx->peer[r] : nullptr;
+    for (int r = 0; r < ctx->nranks; ++r) if (!P.peer[r]) return SHINE_ERR_INVALID_ARG;      // connect() first
+    ctx->step += 1;
+    P.nranks = ctx->nranks; P.rank = ctx->rank; P.step = ctx->step; P.max_floats = ctx->max_floats; P.dec_floats = dec_floats;
+    P.dec = dec_grads; P.num_levels = num_levels; P.feature_dim = feature_dim;
+    DeviceGuard guard(ctx->local);
+    int64_t blocks = (most + 511) / 512;
+    if (blocks > 32) blocks = 32;
+    if (blocks < 1) blocks = 1;
+    p2p_exchange_kernel<<<(unsigned)blocks, 512, 0, (cudaStream_t)stream>>>(P);
+    return (int)cudaGetLastError();
+}
+
+int shine_p2p_timeouts(shine_p2p* ctx, int32_t* out_count) {
+    if (!ctx || !out_count) return SHINE_ERR_INVALID_ARG;
+    DeviceGuard guard(ctx->local);
+    uint32_t v = 0;
+    cudaError_t e = cudaMemcpy(&v, ctx->local + kCtrlOff + 4, sizeof(v), cudaMemcpyDeviceToHost);
+    *out_count = (int32_t)v;
+    return (int)e;
+}
+
+int shine_p2p_destroy(shine_p2p* ctx) {
+    if (!ctx) return SHINE_OK;
+    DeviceGuard guard(ctx->local);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < ctx->nranks; ++r)
+        if (ctx->opened[r] && ctx->peer[r]) cudaIpcCloseMemHandle(ctx->peer[r]);
+    cudaFree(ctx->local);
+    delete ctx;
+    return SHINE_OK;
+}
+
+}  // extern "C"

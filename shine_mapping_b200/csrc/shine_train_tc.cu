@@ -293,9 +293,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) sdf_train_tc_kernel(const __gri
                     b.tx = qk[3 * i]; b.ty = qk[3 * i + 1]; b.tz = qk[3 * i + 2];
                     b.ux = __fsub_rn(1.0f, b.tx); b.uy = __fsub_rn(1.0f, b.ty); b.uz = __fsub_rn(1.0f, b.tz);
                     float* gb = grad_base(lv, (uint32_t)(blockIdx.x * kGSWarps + warp + r), kF) + 4 * half;
+                    // w_c = (X * Y) * Z in the reference's association; the four X*Y products are shared by the z pair
+                    const float xy[4] = {__fmul_rn(b.ux, b.uy), __fmul_rn(b.ux, b.ty), __fmul_rn(b.tx, b.uy), __fmul_rn(b.tx, b.ty)};
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const float w = b.w(c);
+                        const float w = __fmul_rn(xy[c >> 1], (c & 1) ? b.tz : b.uz);
                         red_add_f4(gb + (int64_t)ids[c] * kF, w * dx[0], w * dx[1], w * dx[2], w * dx[3]);
                     }
                 }

@@ -68,6 +68,52 @@ class NcclComm:
             self._comm = None
 
 
+class P2PExchange:
+    """The step's exchange as one kernel over NVLink peer memory (`csrc/shine_p2p.cu`): IPC-shared buffers, flags instead of
+    a collective library.  `SdfTrainer(p2p=...)` uses it for [decoder | boundary rows] in place of pack -> NCCL -> unpack."""
+
+    def __init__(self, rank: int, world: int, device: torch.device, max_floats: int, group=None):
+        import ctypes as C
+        from . import _abi
+        self.rank, self.world, self.device = rank, world, torch.device(device)
+        lib = _abi.lib()
+        handle = (C.c_ubyte * 64)()
+        ctx = C.c_void_p()
+        _abi.check(lib.shine_p2p_create(world, rank, self.device.index or 0, int(max_floats), handle, C.byref(ctx)),
+                   "shine_p2p_create")
+        handles = [None] * world
+        if world > 1:
+            dist.all_gather_object(handles, bytes(handle), group=group)
+        else:
+            handles = [bytes(handle)]
+        blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+        _abi.check(lib.shine_p2p_connect(ctx, blob), "shine_p2p_connect")
+        if world > 1:
+            dist.barrier(group=group)            # every rank has mapped every buffer before the first step
+        self._ctx, self._lib, self._abi, self._C = ctx, lib, _abi, C
+
+    def exchange(self, dec_flat: torch.Tensor, plan, table_grads):
+        """In place: dec_flat and the plan's rows of table_grads become the sums over all ranks."""
+        C = self._C
+        if plan is not None and plan.total_floats > plan.dec_floats:
+            desc, levels, fdim = plan.descriptor(table_grads), len(table_grads), plan.feature_dim
+            arg = C.byref(desc)
+        else:
+            arg, levels, fdim = None, 0, 8
+        self._abi.check(self._lib.shine_p2p_exchange(self._ctx, self._abi.ptr(dec_flat), dec_flat.numel(), arg, levels, fdim,
+                                                     self._abi.stream_ptr(dec_flat.device)), "shine_p2p_exchange")
+
+    def timeouts(self) -> int:
+        n = self._C.c_int32(0)
+        self._abi.check(self._lib.shine_p2p_timeouts(self._ctx, self._C.byref(n)), "shine_p2p_timeouts")
+        return int(n.value)
+
+    def close(self):
+        if self._ctx:
+            self._lib.shine_p2p_destroy(self._ctx)
+            self._ctx = None
+
+
 def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous, balanced slice [begin, end) of an n-point batch for `rank` (sizes differ by at most 1)."""
     base, rem = divmod(n, world)

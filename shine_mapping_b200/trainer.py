@@ -28,7 +28,7 @@ def _align4(n: int) -> int:
 
 class SdfTrainer:
     def __init__(self, config: SHINEConfig, octree: FeatureOctree, decoder: Decoder, process_group=None,
-                 tf32x1: bool = False, shard_mode: str = "replicated", boundary=None, comm=None, tcgen05=None):
+                 tf32x1: bool = False, shard_mode: str = "replicated", boundary=None, comm=None, tcgen05=None, p2p=None):
         """shard_mode (multi-GPU, see dist.py / partition.py): "replicated" = every rank holds the whole table and a
         slice of the point batch -> all-reduce the whole flat gradient; "spatial" = every rank owns a Morton-prefix
         range of ONE map and the samples inside it (BASELINE config 5) -> ONE all-reduce over
@@ -39,6 +39,7 @@ class SdfTrainer:
         self.config, self.octree, self.decoder = config, octree, decoder
         self.shard_mode = shard_mode
         self.boundary, self.comm = boundary, comm
+        self.p2p = p2p              # dist.P2PExchange: the spatial exchange as one NVLink peer-memory kernel
         # gradient replicas for small hot levels (see FeatureOctree._replicas_for); on by default for big batches
         self.use_replicas = os.environ.get("SHINE_FUSED_REPLICAS", "1") != "0"
         self.group = process_group
@@ -180,6 +181,10 @@ class SdfTrainer:
     def all_reduce_grads(self):
         """The step's exchange, ONE sum collective (the 1/N_global is already in the per-point gradient scale):
         replicated -> the whole flat gradient; spatial -> [decoder | rows shared with other ranks]."""
+        if self.p2p is not None and self.shard_mode == "spatial":
+            if self.p2p.world > 1:
+                self.p2p.exchange(self.dec_flat, self.boundary, self.table_grads)
+            return
         world = self.comm.world if self.comm is not None else (
             torch.distributed.get_world_size(self.group)
             if torch.distributed.is_available() and torch.distributed.is_initialized() else 1)

@@ -110,8 +110,22 @@ def _nccl_worker(rank, world, port, out_dir):
     h = tr.submit_host_step(batch[0][m].pin_memory(), batch[1][m].pin_memory(), n_norm=batch[0].shape[0], exchange=True)
     h.result()
     check_rank_against_global([g.detach().cpu().numpy() for g in tr.table_grads], keys, key_to_row, res_glob)
+    # the same exchange as ONE NVLink peer-memory kernel (IPC buffers + flags, no NCCL) — three steps in a row so that both
+    # buffer parities and the flag hand-over between consecutive steps are exercised
+    p2p = sdist.P2PExchange(rank, world, torch.device(dev), plan.total_floats)
+    tr2 = SdfTrainer(cfg, octree, decoder, shard_mode="spatial", boundary=plan, p2p=p2p)
+    for _ in range(3):
+        tr2.zero_grad()
+        loss2 = tr2.forward_backward(batch[0][m].to(dev), batch[1][m].to(dev), None, n_norm=batch[0].shape[0]).clone()
+        tr2.all_reduce_grads()
+        comm.all_reduce(loss2.view(1))
+        torch.cuda.synchronize()
+        check_rank_against_global([g.detach().cpu().numpy() for g in tr2.table_grads], keys, key_to_row, res_glob)
+        _check_decoder_and_loss(tr2, float(loss2), res_glob)
+    assert p2p.timeouts() == 0
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     dist.barrier()
+    p2p.close()
     comm.close()
     dist.destroy_process_group()
 
