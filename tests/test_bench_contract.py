@@ -44,3 +44,17 @@ def test_gpu_arm_refuses_to_run_without_cuda():
     r = _run(["--steps", "1", "--warmup", "1", "--n-azimuth", "64"])
     assert r.returncode != 0
     assert "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_both_arms_describe_the_same_config():
+    """The reference arm steps the same workload with the same points per step as our arm: identical `config` objects
+    (same_config must be true)."""
+    import bench
+    r = _run(["--impl", "reference", "--steps", "1", "--warmup", "0", "--n-azimuth", "64"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref = json.loads(r.stdout.strip().splitlines()[-1])
+    cfg, octree, decoder, pool = bench.build_workload("cpu", 0, 1, 64)
+    ours = bench.shared_config(cfg, 64, len(pool), len(pool), 1, [int(p.shape[0]) for p in octree.hier_features])
+    assert ref["config"] == ours
+    assert ref["config"]["points_per_step_per_gpu"] == len(pool) == ref["config"]["global_points_per_step"]
+    assert str(len(pool)) in ref["cpu_baseline"]["sample"]
