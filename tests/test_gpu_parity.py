@@ -423,9 +423,11 @@ def _trainer_step(case, tcgen05, freeze=False):
 def test_tcgen05_train_step_matches_oracle(levels, poly, weighted, reduction, n_batch):
     """SHINE_FLAG_TCGEN05 on shine_sdf_bce_step: decoder forward / dgrad / wgrad as tcgen05.mma on 128-point tiles
     (operands in shared memory, accumulators in TMEM), same tolerances as the mma.sync kernel."""
+    from tests.parity_utils import drop_relu_kink_points
     case = make_case(n_points=2500, n_batch=n_batch, feat_levels=levels, seed=40 + levels, poly=poly, weighted=weighted,
                      reduction=reduction, n_frames=2 if n_batch > 10000 else 1)
-    print(compare_step(_trainer_step(case, True), run_oracle_step(case)))
+    case, dropped = drop_relu_kink_points(case)
+    print("points on a ReLU kink dropped:", dropped, compare_step(_trainer_step(case, True), run_oracle_step(case)))
 
 
 def test_tcgen05_train_step_frozen_decoder():
