@@ -304,22 +304,31 @@ class SdfTrainer:
         pl = getattr(self, "_pipe", None)
         if pl is None or pl["cap"] < n or pl["sig"] != self._sig:
             pl = {"cap": n, "sig": self._sig, "k": 0, "copy": torch.cuda.Stream(device=dev),
+                  "copy2": torch.cuda.Stream(device=dev),
                   "slots": [{"coord": torch.empty(n, 3, device=dev), "label": torch.empty(n, device=dev),
                              "weight": torch.empty(n, device=dev), "free": None,
                              "loss_h": torch.zeros(1).pin_memory()} for _ in range(2)]}
             self._pipe = pl
         slot = pl["slots"][pl["k"] & 1]
         pl["k"] += 1
-        main, copy = torch.cuda.current_stream(dev), pl["copy"]
+        main, copy, copy2 = torch.cuda.current_stream(dev), pl["copy"], pl["copy2"]
         if slot["free"] is not None:
             copy.wait_event(slot["free"])            # the kernels that read this slot two steps ago are done
+            copy2.wait_event(slot["free"])
+        # two copy streams: the coordinates (3/4 of the bytes) are split in halves that travel concurrently
+        half = (n // 2) & ~63
         with torch.cuda.stream(copy):
-            slot["coord"][:n].copy_(coord_h, non_blocking=True)
+            slot["coord"][:half].copy_(coord_h[:half], non_blocking=True)
             slot["label"][:n].copy_(label_h, non_blocking=True)
-            if weighted:
-                slot["weight"][:n].copy_(weight_h, non_blocking=True)
             copied = torch.cuda.Event()
             copied.record(copy)
+        with torch.cuda.stream(copy2):
+            slot["coord"][half:n].copy_(coord_h[half:], non_blocking=True)
+            if weighted:
+                slot["weight"][:n].copy_(weight_h, non_blocking=True)
+            copied2 = torch.cuda.Event()
+            copied2.record(copy2)
+        main.wait_event(copied2)
         main.wait_event(copied)
         self.zero_grad()
         self.forward_backward(slot["coord"][:n], slot["label"][:n], slot["weight"][:n] if weighted else None,
