@@ -429,6 +429,57 @@ def small_batch_records(cfg, octree, decoder, pool, dev, sizes=(4096, 8192), ite
     return out
 
 
+def other_config_records(dev):
+    """Short records for the BASELINE.json configs that are not the headline workload (their parity is covered by tests):
+    C1 = 10 k ray-sampled points, 2-level octree (the reference's CPU-runnable case): GPU step next to the oracle's CPU step;
+    C4 = incremental mapping with the regularisation terms (per-touched-row kernels): time per frame of the loop."""
+    from shine_mapping_b200 import Decoder, FeatureOctree, SHINEConfig, SdfTrainer, synth
+    from shine_mapping_b200.incre_loop import run_shine_mapping_incremental
+    out = {}
+    # ---- C1 ----
+    cfg = workload_config(str(dev)); cfg.name = "c1_10k_points_2_levels"; cfg.tree_level_feat = 2
+    torch.manual_seed(42)
+    octree, decoder = FeatureOctree(cfg), Decoder(cfg)
+    pool = synth.build_scene_map(cfg, octree, n_azimuth=256, n_frames=1, seed=42, device=str(dev))
+    gen = torch.Generator(device=dev).manual_seed(1)
+    coord, label, _ = pool.get_batch(10000, gen)
+    tr = SdfTrainer(cfg, octree, decoder)
+    for _ in range(5):
+        tr.zero_grad(); tr.forward_backward(coord, label, None)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(50):
+        tr.zero_grad(); tr.forward_backward(coord, label, None)
+    e1.record(); torch.cuda.synchronize(dev)
+    gpu_ms = e0.elapsed_time(e1) / 50
+    orc, o, dec = oracle_from_octree(octree, decoder)
+    torch.set_num_threads(os.cpu_count() or 1)
+    cb = (coord.cpu(), label.cpu(), None)
+    orc.train_step(o, dec, *cb, cfg.sigma_sigmoid, False, "mean")
+    t0 = time.perf_counter(); res = orc.train_step(o, dec, *cb, cfg.sigma_sigmoid, False, "mean"); cpu_s = time.perf_counter() - t0
+    out["c1"] = {"workload": cfg.name, "points": 10000, "table_rows": [int(p.shape[0]) for p in octree.hier_features],
+                 "gpu_ms_per_step": gpu_ms, "gpu_points_per_s": 10000 / (gpu_ms * 1e-3),
+                 "cpu_ms_per_step": cpu_s * 1e3, "cpu_points_per_s": 10000 / cpu_s,
+                 "loss_rel_vs_oracle": abs(float(tr.loss) - float(res["loss"])) / abs(float(res["loss"]))}
+    # ---- C4 ----
+    cfg4 = workload_config(str(dev)); cfg4.name = "c4_incremental_with_regularisation"
+    cfg4.bs, cfg4.iters, cfg4.continual_learning_reg, cfg4.lambda_forget, cfg4.loss_reduction = 4096, 50, True, 1e4, "sum"
+    torch.manual_seed(42)
+    octree4, decoder4 = FeatureOctree(cfg4), Decoder(cfg4)
+    frames = [f[:3] for f in synth.generate_scans(cfg4, 1024, 6, 2.0, 42, str(dev))]
+    run_shine_mapping_incremental(cfg4, octree4, decoder4, frames[:1])            # warm-up frame (kernel attributes, allocator)
+    torch.cuda.synchronize(dev); t0 = time.perf_counter()
+    hist = run_shine_mapping_incremental(cfg4, octree4, decoder4, frames[1:])
+    torch.cuda.synchronize(dev); dt = time.perf_counter() - t0
+    out["c4"] = {"workload": cfg4.name, "frames": len(frames) - 1, "iters_per_frame": cfg4.iters, "bs": cfg4.bs,
+                 "samples_per_frame": int(frames[1][0].shape[0]),
+                 "s_per_frame": dt / (len(frames) - 1), "frame_content": "octree.update (GPU build kernels) + 50 x {get_batch, fused "
+                 "step, touched-row regulariser, Adam} + feature-importance sweep over the frame's pool",
+                 "rows_last": hist[-1]["rows"], "bce_first_last": [hist[-1]["bce_first"], hist[-1]["bce_last"]]}
+    return out
+
+
 def run_ours(args):
     from shine_mapping_b200 import SdfTrainer, _abi, dist as sdist
     rank, world, local = sdist.init_from_env("nccl")
@@ -593,6 +644,7 @@ def run_ours(args):
                                 "kind": "port", "sample": f"first {sample} points of the step's batch, 1 warm-up + 3 "
                                                            "timed oracle steps (Python-dict lookup + torch CPU autograd)"}
         line["parity"] = parity_block(orc, o, dec, trainer, octree, decoder, batches[0], sample, cfg.sigma_sigmoid)
+        line["configs"] = other_config_records(dev)
     print(json.dumps(line), flush=True)
 
 
