@@ -54,7 +54,7 @@ __device__ __forceinline__ float4 ld_peer_f4(const float* p) {
     return v;
 }
 
-__global__ void __launch_bounds__(512) p2p_exchange_kernel(const __grid_constant__ P2PParams P) {
+__global__ void __launch_bounds__(1024) p2p_exchange_kernel(const __grid_constant__ P2PParams P) {
     unsigned char* mine_base = P.peer[P.rank];
     float* mine = data_of(mine_base, P.step, P.max_floats);
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gs = (int64_t)gridDim.x * blockDim.x;
@@ -71,34 +71,38 @@ __global__ void __launch_bounds__(512) p2p_exchange_kernel(const __grid_constant
                 reinterpret_cast<const float4*>(b.table + (int64_t)b.rows[r] * P.feature_dim)[part];
         }
     }
-    // 2. publish (last block)
+    // 2. publish: one system-scope fence by the publishing threads after the block(s) have finished packing (the
+    //    barrier / the device-scope fence + counter make the other threads' stores cumulative with it)
     volatile uint32_t* ctrl = reinterpret_cast<volatile uint32_t*>(mine_base + kCtrlOff);
     __shared__ int is_last;
-    __threadfence_system();                 // every thread: its packed values are visible to the peers before the flag
     __syncthreads();
-    if (threadIdx.x == 0) {
-        const uint32_t prev = atomicAdd(const_cast<uint32_t*>(ctrl), 1u);
-        is_last = prev == gridDim.x - 1;
+    if (gridDim.x == 1) {
+        is_last = 1;
+    } else {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const uint32_t prev = atomicAdd(const_cast<uint32_t*>(ctrl), 1u);
+            is_last = prev == gridDim.x - 1;
+            if (is_last) ctrl[0] = 0u;                                    // ready for the next launch
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    if (is_last) {
-        if (threadIdx.x == 0) ctrl[0] = 0u;                               // ready for the next launch
+    if (is_last && threadIdx.x < P.nranks) {
         __threadfence_system();
-        if (threadIdx.x < P.nranks) {
-            volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(P.peer[threadIdx.x] + (size_t)P.rank * kFlagStride);
-            *flag = P.step;
-        }
+        uint32_t* flag = reinterpret_cast<uint32_t*>(P.peer[threadIdx.x] + (size_t)P.rank * kFlagStride);
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(P.step) : "memory");
     }
-    // 3. wait for every rank's publication of this step
+    // 3. wait for every rank's publication of this step (acquire loads of the local flags the peers write)
     if (threadIdx.x < P.nranks) {
-        volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(mine_base + (size_t)threadIdx.x * kFlagStride);
+        const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine_base + (size_t)threadIdx.x * kFlagStride);
         long long spin = 0;
-        while ((int32_t)(*flag - P.step) < 0) {
+        uint32_t seen;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
             if (++spin > kSpinLimit) { atomicAdd(const_cast<uint32_t*>(ctrl) + 1, 1u); break; }
-        }
+        } while ((int32_t)(seen - P.step) < 0);
     }
     __syncthreads();
-    __threadfence_system();
     // 4. reduce, fixed rank order, in place
     for (int64_t i = gt; i < P.dec_floats / 4; i += gs) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -193,10 +197,10 @@ int shine_p2p_exchange(shine_p2p* ctx, float* dec_grads, int64_t dec_floats, con
     P.nranks = ctx->nranks; P.rank = ctx->rank; P.step = ctx->step; P.max_floats = ctx->max_floats; P.dec_floats = dec_floats;
     P.dec = dec_grads; P.num_levels = num_levels; P.feature_dim = feature_dim;
     DeviceGuard guard(ctx->local);
-    int64_t blocks = (most + 511) / 512;
+    // latency-bound for the usual few KB: one block (no grid hand-shake); more blocks only for big boundary sets
+    int64_t blocks = most <= 16 * 1024 ? 1 : (most + 8191) / 8192;
     if (blocks > 32) blocks = 32;
-    if (blocks < 1) blocks = 1;
-    p2p_exchange_kernel<<<(unsigned)blocks, 512, 0, (cudaStream_t)stream>>>(P);
+    p2p_exchange_kernel<<<(unsigned)blocks, 1024, 0, (cudaStream_t)stream>>>(P);
     return (int)cudaGetLastError();
 }
 
