@@ -285,6 +285,7 @@ def time_steps(trainer, batches, steps, flush_buf, n_norm, dev, all_reduce=True)
         ev[k][4].record()
     torch.cuda.synchronize(dev)
     mean = statistics.mean
+    time_steps.last_exchange_ms = mean(e[3].elapsed_time(e[4]) for e in ev)      # exchange + waiting for the slowest rank
     return (mean(e[0].elapsed_time(e[4]) for e in ev), mean(e[1].elapsed_time(e[2]) for e in ev),
             mean(e[2].elapsed_time(e[3]) for e in ev))
 
@@ -534,6 +535,10 @@ def run_ours(args):
     step_ms = sdist.max_over_ranks(step_ms, dev)
     kern_ms_max = sdist.max_over_ranks(kern_ms, dev)
     red_ms_max = sdist.max_over_ranks(red_ms, dev)
+    exch_ms = getattr(time_steps, "last_exchange_ms", 0.0)
+    exch_ms_max = sdist.max_over_ranks(exch_ms, dev)
+    exch_ms_min = -sdist.max_over_ranks(-exch_ms, dev)
+    kern_ms_min = -sdist.max_over_ranks(-kern_ms, dev)
     # nvidia-smi cannot sample faster than ~20 ms: keep the SAME steps running (not counted) so that the sampled
     # window under load is ~0.5 s.  The count is derived from the rank-agreed step time: every rank issues the same
     # number of collectives.
@@ -604,6 +609,9 @@ def run_ours(args):
                        f"one map, Morton-prefix ranges x{world}; ONE exchange per step over [decoder grads | "
                        "gradients of corner rows shared between ranges] (see partition.exchange)",
                        "partition": part_info,
+                       "exchange_ms": {"max_over_ranks": exch_ms_max, "min_over_ranks": exch_ms_min,
+                                       "note": "events around the exchange: its latency + the wait for the slowest rank's kernel"},
+                       "kernel_ms_min_over_ranks": kern_ms_min,
                        "l2": "flushed between timed steps (256 MiB write, not timed)",
                        "timed_step": "grad memset + fused fwd+loss+bwd kernel + replica fold (+ all-reduce when N>1)"},
         # the C2 map (2.75 MB of features) lives in L2: the kernel's physical bound there is the L1TEX LSU data pipe

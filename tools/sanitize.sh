@@ -1,5 +1,5 @@
-# compute-sanitizer over one small fused step + query fwd/bwd + adam (memcheck, racecheck, synccheck)
+# compute-sanitizer over small invocations of every kernel family (memcheck everywhere, racecheck on the shared-memory heavy ones)
 set -x
-for tool in memcheck racecheck synccheck; do
-  timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "ragged_batch_sizes and 17 or fused_step_matches_oracle and 2-True or adam_kernel" 2>&1 | tail -6
-done
+SEL="ragged_batch_sizes and 17 or fused_step_matches_oracle and 2-True or adam_kernel or fused_eikonal_step_matches_oracle and 2-True or tcgen05_train_step_matches_oracle and 100 or regularization_and_importance or three_ranges or cuda_update_matches or hash_insert_reports"
+timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests -m gpu -q -x -k "$SEL" 2>&1 | tail -8
+timeout 1200 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "fused_step_matches_oracle and 2-True or fused_eikonal_step_matches_oracle and 2-True" 2>&1 | tail -6
