@@ -295,11 +295,15 @@ const char* shine_comm_last_error(void);
  * connect -> exchange every step (all ranks, same order).  plan offsets are relative to the exchange buffer whose first
  * dec_floats floats are the decoder segment, exactly as for shine_boundary_pack.  A peer that never shows up is a
  * counted timeout (shine_p2p_timeouts), not a hang. */
+typedef struct shine_boundary_inverse {
+    const int32_t* row_of_slot[SHINE_MAX_LEVELS];   /* [slots of the level] local row holding that shared corner, -1 if none */
+    int32_t slots[SHINE_MAX_LEVELS];                /* length of the level's globally agreed boundary list           */
+} shine_boundary_inverse;
 typedef struct shine_p2p shine_p2p;
 int shine_p2p_create(int32_t nranks, int32_t rank, int32_t device, int64_t max_floats, void* out_handle64, shine_p2p** out);
 int shine_p2p_connect(shine_p2p* ctx, const void* handles /* nranks x 64 B, rank order */);
 int shine_p2p_exchange(shine_p2p* ctx, float* dec_grads, int64_t dec_floats, const shine_boundary* plan,
-                       int32_t num_levels, int32_t feature_dim, void* stream);
+                       const shine_boundary_inverse* inverse, int32_t num_levels, int32_t feature_dim, void* stream);
 int shine_p2p_timeouts(shine_p2p* ctx, int32_t* out_count);
 int shine_p2p_destroy(shine_p2p* ctx);
 

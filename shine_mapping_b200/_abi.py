@@ -85,6 +85,10 @@ class ShineBuild(C.Structure):
                 ("lv", ShineBuildLevel * MAX_LEVELS)]
 
 
+class ShineBoundaryInverse(C.Structure):
+    _fields_ = [("row_of_slot", C.c_void_p * MAX_LEVELS), ("slots", C.c_int32 * MAX_LEVELS)]
+
+
 # name -> (restype, argtypes); every symbol declared in include/shine_b200.h
 _vp, _i64, _i32, _u32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_float
 _OCT, _DEC = C.POINTER(ShineOctree), C.POINTER(ShineDecoder)
@@ -124,7 +128,7 @@ SYMBOLS = {
     "shine_comm_last_error": (C.c_char_p, []),
     "shine_p2p_create": (C.c_int, [_i32, _i32, _i32, _i64, _vp, C.POINTER(C.c_void_p)]),
     "shine_p2p_connect": (C.c_int, [_vp, _vp]),
-    "shine_p2p_exchange": (C.c_int, [_vp, _vp, _i64, C.POINTER(ShineBoundary), _i32, _i32, _vp]),
+    "shine_p2p_exchange": (C.c_int, [_vp, _vp, _i64, C.POINTER(ShineBoundary), C.POINTER(ShineBoundaryInverse), _i32, _i32, _vp]),
     "shine_p2p_timeouts": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
     "shine_p2p_destroy": (C.c_int, [_vp]),
     "shine_adam_step": (C.c_int, [C.POINTER(ShineAdamTensor), _i32, _f32, _f32, _f32, _i32, _i32, _vp]),

@@ -41,6 +41,8 @@ struct P2PParams {
     int64_t max_floats, dec_floats;
     float* dec;                         // decoder segment (in place)
     shine_boundary plan;                // table-gradient rows shared with other ranks
+    shine_boundary_inverse inv;         // slot -> local row (or -1) per level: lets the reduce run as ONE flat loop
+    int64_t total_floats;               // decoder segment + every level's slots
     int32_t num_levels, feature_dim;
 };
 
@@ -103,27 +105,31 @@ __global__ void __launch_bounds__(1024) p2p_exchange_kernel(const __grid_constan
         } while ((int32_t)(seen - P.step) < 0);
     }
     __syncthreads();
-    // 4. reduce, fixed rank order, in place
-    for (int64_t i = gt; i < P.dec_floats / 4; i += gs) {
+    // 4. reduce, fixed rank order, in place.  ONE flat loop over [decoder | level 0 slots | level 1 slots | ...]: every
+    //    NVLink load of a pass is independent of every other (per-level loops would serialise one round trip per level)
+    const int64_t n4 = P.total_floats / 4;
+    for (int64_t i = gt; i < n4; i += gs) {
+        const int64_t fo = 4 * i;                                    // float offset in the exchange buffer
+        float* dst = nullptr;
+        if (fo < P.dec_floats) {
+            dst = P.dec + fo;
+        } else {
+            int l = 0;
+#pragma unroll
+            for (int q = 1; q < SHINE_MAX_LEVELS; ++q)
+                if (q < P.num_levels && fo >= P.plan.lv[q].offset) l = q;
+            const int64_t rel = fo - P.plan.lv[l].offset;
+            const int slot = (int)(rel / P.feature_dim), within = (int)(rel % P.feature_dim);
+            const int row = P.inv.row_of_slot[l][slot];
+            if (row >= 0) dst = P.plan.lv[l].table + (int64_t)row * P.feature_dim + within;
+        }
+        if (!dst) continue;                                            // a corner this rank does not hold
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         for (int r = 0; r < P.nranks; ++r) {
-            const float4 v = ld_peer_f4(data_of(P.peer[r], P.step, P.max_floats) + 4 * i);
+            const float4 v = ld_peer_f4(data_of(P.peer[r], P.step, P.max_floats) + fo);
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
-        reinterpret_cast<float4*>(P.dec)[i] = acc;
-    }
-    for (int l = 0; l < P.num_levels; ++l) {
-        const shine_boundary_level& b = P.plan.lv[l];
-        for (int64_t i = gt; i < (int64_t)b.count * lp; i += gs) {
-            const int row = (int)(i / lp), part = (int)(i % lp);
-            const int64_t off = b.offset + (int64_t)b.slots[row] * P.feature_dim;
-            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int r = 0; r < P.nranks; ++r) {
-                const float4 v = ld_peer_f4(data_of(P.peer[r], P.step, P.max_floats) + off + 4 * part);
-                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-            }
-            reinterpret_cast<float4*>(b.table + (int64_t)b.rows[row] * P.feature_dim)[part] = acc;
-        }
+        *reinterpret_cast<float4*>(dst) = acc;
     }
 }
 
@@ -176,21 +182,25 @@ int shine_p2p_connect(shine_p2p* ctx, const void* handles) {
     return SHINE_OK;
 }
 
-int shine_p2p_exchange(shine_p2p* ctx, float* dec_grads, int64_t dec_floats, const shine_boundary* plan, int32_t num_levels,
-                       int32_t feature_dim, void* stream) {
+int shine_p2p_exchange(shine_p2p* ctx, float* dec_grads, int64_t dec_floats, const shine_boundary* plan,
+                       const shine_boundary_inverse* inverse, int32_t num_levels, int32_t feature_dim, void* stream) {
     if (!ctx || !dec_grads || dec_floats < 0 || (dec_floats & 3) || num_levels < 0 || num_levels > SHINE_MAX_LEVELS)
         return SHINE_ERR_INVALID_ARG;
-    if (num_levels > 0 && (!plan || feature_dim < 4 || (feature_dim & 3))) return SHINE_ERR_INVALID_ARG;
+    if (num_levels > 0 && (!plan || !inverse || feature_dim < 4 || (feature_dim & 3))) return SHINE_ERR_INVALID_ARG;
     P2PParams P;
-    int64_t most = dec_floats / 4, end = dec_floats;
+    int64_t end = dec_floats;
     for (int l = 0; l < num_levels; ++l) {
         const shine_boundary_level& b = plan->lv[l];
-        if (b.count < 0 || (b.count > 0 && (!b.table || !b.rows || !b.slots)) || (b.offset & 3) || b.offset < dec_floats)
-            return SHINE_ERR_INVALID_ARG;
-        if ((int64_t)b.count * (feature_dim / 4) > most) most = (int64_t)b.count * (feature_dim / 4);
+        if (b.count < 0 || (b.count > 0 && (!b.table || !b.rows || !b.slots)) || (b.offset & 3) || b.offset != end)
+            return SHINE_ERR_INVALID_ARG;                              // levels are laid out back to back
+        if (inverse->slots[l] < 0 || (inverse->slots[l] > 0 && !inverse->row_of_slot[l])) return SHINE_ERR_INVALID_ARG;
+        end += (int64_t)inverse->slots[l] * feature_dim;
         P.plan.lv[l] = b;
+        P.inv.row_of_slot[l] = inverse->row_of_slot[l]; P.inv.slots[l] = inverse->slots[l];
     }
-    (void)end;
+    if (end > ctx->max_floats) return SHINE_ERR_INVALID_ARG;
+    P.total_floats = end;
+    const int64_t most = end / 4;
     for (int r = 0; r < kMaxRanks; ++r) P.peer[r] = r < ctx->nranks ? ctx->peer[r] : nullptr;
     for (int r = 0; r < ctx->nranks; ++r) if (!P.peer[r]) return SHINE_ERR_INVALID_ARG;      // connect() first
     ctx->step += 1;

@@ -96,11 +96,17 @@ class P2PExchange:
         """In place: dec_flat and the plan's rows of table_grads become the sums over all ranks."""
         C = self._C
         if plan is not None and plan.total_floats > plan.dec_floats:
-            desc, levels, fdim = plan.descriptor(table_grads), len(table_grads), plan.feature_dim
-            arg = C.byref(desc)
+            key = tuple(t.data_ptr() for t in table_grads)
+            cached = getattr(self, "_desc", None)
+            if cached is None or cached[0] != key:          # building the ctypes structs costs tens of us of Python
+                cached = (key, plan.descriptor(table_grads), plan.inverse_descriptor(), len(table_grads), plan.feature_dim)
+                self._desc = cached
+            _, desc, inv, levels, fdim = cached
+            arg, iarg = C.byref(desc), C.byref(inv)
         else:
-            arg, levels, fdim = None, 0, 8
-        self._abi.check(self._lib.shine_p2p_exchange(self._ctx, self._abi.ptr(dec_flat), dec_flat.numel(), arg, levels, fdim,
+            arg, iarg, levels, fdim = None, None, 0, 8
+        dec_n = plan.dec_floats if plan is not None else dec_flat.numel()
+        self._abi.check(self._lib.shine_p2p_exchange(self._ctx, self._abi.ptr(dec_flat), dec_n, arg, iarg, levels, fdim,
                                                      self._abi.stream_ptr(dec_flat.device)), "shine_p2p_exchange")
 
     def timeouts(self) -> int:

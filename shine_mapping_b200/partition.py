@@ -60,7 +60,7 @@ class BoundaryPlan:
         n_levels = len(per_rank_level_keys[rank])
         self.rank, self.world, self.feature_dim = rank, world, feature_dim
         self.dec_floats = dec_floats
-        self.rows, self.slots, self.owned, self.counts, self.offsets = [], [], [], [], []
+        self.rows, self.slots, self.owned, self.counts, self.offsets, self.inverse = [], [], [], [], [], []
         off = dec_floats
         for lvl in range(n_levels):        # coarse -> fine, like hier_features
             keys_all = torch.cat([per_rank_level_keys[r][lvl].cpu() for r in range(world)])
@@ -77,6 +77,9 @@ class BoundaryPlan:
             first = torch.full((uniq.numel(),), world, dtype=torch.int64)
             first.scatter_reduce_(0, inv, ranks_all, reduce="amin")
             owner_of_shared = first[cnt > 1]
+            inv = torch.full((int(shared.numel()),), -1, dtype=torch.int32)
+            inv[slots] = rows.to(torch.int32)
+            self.inverse.append(inv)
             self.rows.append(rows.to(torch.int32)); self.slots.append(slots.to(torch.int32))
             self.owned.append(owner_of_shared[slots] == rank)
             self.counts.append(int(shared.numel()))
@@ -88,7 +91,15 @@ class BoundaryPlan:
         self.rows = [t.to(device) for t in self.rows]
         self.slots = [t.to(device) for t in self.slots]
         self.owned = [t.to(device) for t in self.owned]
+        self.inverse = [t.to(device) for t in self.inverse]
         return self
+
+    def inverse_descriptor(self) -> _abi.ShineBoundaryInverse:
+        d = _abi.ShineBoundaryInverse()
+        for lvl, inv in enumerate(self.inverse):
+            d.row_of_slot[lvl] = inv.data_ptr() if inv.numel() else None
+            d.slots[lvl] = int(inv.numel())
+        return d
 
     def descriptor(self, tables, buf_base_offset: int = 0) -> _abi.ShineBoundary:
         """C descriptor for `tables` (coarse -> fine list of [rows, F] tensors).  Offsets are relative to the buffer
