@@ -98,6 +98,29 @@ def test_two_gpu_data_parallel_matches_oracle(tmp_path, built_lib):
     assert abs(float(np.load(tmp_path / "loss.npy")) - want["loss"]) <= 2e-5 * abs(want["loss"])
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_abi_launches_on_the_device_that_owns_the_tensors(built_lib):
+    """model on cuda:1 while the current device is cuda:0 — every entry point must launch on cuda:1 (device
+    looked up from the pointers, per-device function-attribute caches), and a batch on the wrong device is an argument error."""
+    from shine_mapping_b200 import SdfTrainer, _abi
+    from tests.parity_utils import compare_step, run_oracle_step
+    assert torch.cuda.current_device() == 0
+    case = make_case(n_points=2000, n_batch=2500, feat_levels=4, seed=77)
+    cfg, octree, dec = build_cuda_models(case, "cuda:1")
+    coord = torch.from_numpy(case["coord"]).to("cuda:1"); label = torch.from_numpy(case["label"]).to("cuda:1")
+    tr = SdfTrainer(cfg, octree, dec)
+    tr.zero_grad()
+    pred = torch.empty(coord.shape[0], device="cuda:1")
+    loss = tr.forward_backward(coord, label, None, pred_out=pred)
+    torch.cuda.synchronize("cuda:1")
+    assert torch.cuda.current_device() == 0
+    want = run_oracle_step(case)
+    assert abs(float(loss) - want["loss"]) <= 2e-5 * abs(want["loss"])
+    assert np.abs(pred.cpu().numpy() - want["pred"]).max() <= 2e-5 + 1e-5 * np.abs(want["pred"]).max()
+    with pytest.raises(_abi.ShineB200Error):
+        tr.forward_backward(coord.to("cuda:0"), label.to("cuda:0"), None)
+
+
 def test_step_from_host_matches_resident_step(built_lib):
     """The host-buffer entry (pinned memory, chunked H2D overlapped with compute) gives the same loss / gradients
     as one launch on resident inputs."""

@@ -436,3 +436,24 @@ def test_tcgen05_train_step_frozen_decoder():
     want = run_oracle_step(case)
     want["dec_grads"] = {}
     print(compare_step(got, want))
+
+
+def test_two_queries_before_one_backward():
+    """ADVICE r01: the reference queries `coord_near` while the first query's graph is still alive (shine_batch.py:155-160);
+    re-zeroing the trash row inside query_feature must not invalidate the tensors autograd saved for the first query."""
+    case = make_case(n_points=1500, n_batch=600, feat_levels=3, seed=12)
+    cfg, octree, dec = build_cuda_models(case, DEV)
+    c = torch.from_numpy(case["coord"]).to(DEV)
+    f1 = octree.query_feature(c[:300])
+    f2 = octree.query_feature(c[300:600] + 1e-4)
+    (f1.sum() + 2.0 * f2.sum()).backward()
+    g = [p.grad.clone() for p in octree.hier_features]
+    for p in octree.hier_features:
+        p.grad = None
+    octree.query_feature(c[:300]).sum().backward()
+    ga = [p.grad.clone() for p in octree.hier_features]
+    for p in octree.hier_features:
+        p.grad = None
+    (2.0 * octree.query_feature(c[300:600] + 1e-4).sum()).backward()
+    for a, b, p in zip(g, ga, octree.hier_features):
+        assert torch.allclose(a, b + p.grad, rtol=1e-5, atol=1e-7)
