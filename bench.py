@@ -61,7 +61,7 @@ def build_workload(device, rank, world, n_azimuth):
 SCAN_SPACING_M = 25.0    # multi-GPU map: one scan per GPU, 25 m apart along the street (pc_radius 50 m: they overlap)
 
 
-def build_partitioned_workload(device, rank, world, n_azimuth, n_frames=None, exchange="nccl"):
+def build_partitioned_workload(device, rank, world, n_azimuth, n_frames=None, exchange="auto"):
     """N > 1: ONE map of `world` overlapping scans, partitioned by Morton prefix at the coarsest featured level into
     `world` balanced ranges (partition.py).  Every rank generates the same global pool (seeded), keeps the samples of its
     range, grows its own octree from them; corner rows on the faces between ranges are duplicated and exchanged every
@@ -94,8 +94,16 @@ def build_partitioned_workload(device, rank, world, n_azimuth, n_frames=None, ex
     if comm is not None:
         plan.unify_values(list(octree.hier_features), comm.all_reduce)
     p2p = None
-    if world > 1 and exchange == "p2p":
-        p2p = sdist.P2PExchange(rank, world, torch.device(device), plan.total_floats)
+    if world > 1 and exchange in ("p2p", "auto"):
+        # peer-memory exchange when every rank can map every peer's buffer (CUDA IPC); all ranks take the same decision
+        try:
+            p2p = sdist.P2PExchange(rank, world, torch.device(device), plan.total_floats)
+            ok = 1
+        except Exception as exc:       # noqa: BLE001 — e.g. IPC not permitted in this container
+            print(f"[bench] rank {rank}: peer-memory exchange unavailable ({exc}); using the NCCL path", file=sys.stderr)
+            p2p, ok = None, 0
+        if not ok and exchange == "p2p":       # P2PExchange agrees across ranks before raising: every rank lands here together
+            raise SystemExit("--exchange p2p requested but CUDA IPC peer mapping failed")
     info = {"global_pool_samples": global_pool, "scans": n_frames, "scan_spacing_m": SCAN_SPACING_M,
             "boundary_rows": [int(c) for c in plan.counts], "exchange_floats": int(plan.total_floats),
             "exchange": "one NVLink peer-memory kernel (pack + publish + wait + reduce in place), IPC buffers" if p2p else
@@ -671,7 +679,7 @@ def main():
                          "cpu_baseline / parity legs of our arm default to 100000")
     ap.add_argument("--hbm-frames", type=int, default=100, help="frames of the HBM-bound leg's map")
     ap.add_argument("--hbm-points", type=int, default=1 << 20, help="points per step of the HBM-bound leg")
-    ap.add_argument("--exchange", default=os.environ.get("SHINE_EXCHANGE", "nccl"), choices=["nccl", "p2p"],
+    ap.add_argument("--exchange", default=os.environ.get("SHINE_EXCHANGE", "auto"), choices=["auto", "nccl", "p2p"],
                     help="N>1: the step's exchange — NCCL all-reduce through the C ABI, or the one-kernel NVLink peer-memory path")
     ap.add_argument("--no-hbm-leg", action="store_true")
     ap.add_argument("--hbm-only", action="store_true", help="run only the HBM-bound leg and print its object (ncu target)")

@@ -79,18 +79,28 @@ class P2PExchange:
         lib = _abi.lib()
         handle = (C.c_ubyte * 64)()
         ctx = C.c_void_p()
-        _abi.check(lib.shine_p2p_create(world, rank, self.device.index or 0, int(max_floats), handle, C.byref(ctx)),
-                   "shine_p2p_create")
-        handles = [None] * world
+        # every rank walks through the same collectives whatever happens locally, then all agree on the outcome
+        rc = lib.shine_p2p_create(world, rank, self.device.index or 0, int(max_floats), handle, C.byref(ctx))
+        mine = (rc, bytes(handle))
+        everyone = [None] * world
         if world > 1:
-            dist.all_gather_object(handles, bytes(handle), group=group)
+            dist.all_gather_object(everyone, mine, group=group)
         else:
-            handles = [bytes(handle)]
-        blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
-        _abi.check(lib.shine_p2p_connect(ctx, blob), "shine_p2p_connect")
+            everyone = [mine]
+        if rc == 0 and all(r == 0 for r, _ in everyone):
+            blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(h for _, h in everyone))
+            rc = lib.shine_p2p_connect(ctx, blob)
+        elif rc == 0:
+            rc = -1
+        ok = torch.tensor([1 if rc == 0 else 0], dtype=torch.int32, device=self.device if dist.is_initialized() and
+                          dist.get_backend(group) == "nccl" else "cpu")
         if world > 1:
-            dist.barrier(group=group)            # every rank has mapped every buffer before the first step
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)      # also: every rank has mapped every buffer
         self._ctx, self._lib, self._abi, self._C = ctx, lib, _abi, C
+        if int(ok.item()) == 0:
+            self.close()
+            raise _abi.ShineB200Error(f"peer-memory exchange could not be set up (local code {rc}: "
+                                      f"{lib.shine_error_string(rc).decode() if rc > -1000 else rc})")
 
     def exchange(self, dec_flat: torch.Tensor, plan, table_grads):
         """In place: dec_flat and the plan's rows of table_grads become the sums over all ranks."""
@@ -115,7 +125,7 @@ class P2PExchange:
         return int(n.value)
 
     def close(self):
-        if self._ctx:
+        if getattr(self, "_ctx", None):
             self._lib.shine_p2p_destroy(self._ctx)
             self._ctx = None
 
