@@ -40,6 +40,9 @@
 #ifndef SHINE_GATHER_GROUP
 #define SHINE_GATHER_GROUP 2  // levels whose first-probe sectors are in flight together (register pressure vs parallelism)
 #endif
+#ifndef SHINE_SLOT_PREFETCH
+#define SHINE_SLOT_PREFETCH 1  // training kernel: hash + L1 prefetch of the NEXT tile's home slots before this tile's scatter
+#endif
 #ifndef SHINE_TRAIN_MINB
 #define SHINE_TRAIN_MINB 2    // min resident blocks/SM of the training kernel (register cap 65536/(256*MINB))
 #endif
@@ -294,6 +297,19 @@ __global__ void __launch_bounds__(256) query_tangent_kernel(const __grid_constan
     }
 }
 
+// acc[q] = fma(w3, r3[q], fma(w2, r2[q], fma(w1, r1[q], fma(w0, r0[q], acc[q])))) for the 8 channels, two per FFMA2
+__device__ __forceinline__ void blend4(float (&acc)[8], const float (&r0)[8], const float (&r1)[8], const float (&r2)[8],
+                                       const float (&r3)[8], float w0, float w1, float w2, float w3) {
+    const f2_t p0 = f2_pack(w0, w0), p1 = f2_pack(w1, w1), p2 = f2_pack(w2, w2), p3 = f2_pack(w3, w3);
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) {
+        f2_t a = f2_pack(acc[q], acc[q + 1]);
+        a = f2_fma(p0, f2_pack(r0[q], r0[q + 1]), a); a = f2_fma(p1, f2_pack(r1[q], r1[q + 1]), a);
+        a = f2_fma(p2, f2_pack(r2[q], r2[q + 1]), a); a = f2_fma(p3, f2_pack(r3[q], r3[q + 1]), a);
+        f2_unpack(a, acc[q], acc[q + 1]);
+    }
+}
+
 // row-half layout (this lane: 4 channels of its own point) -> A fragment of the 16x8 tile.
 // k-slot t <-> channel 2t, k-slot t+4 <-> channel 2t+1 (the B fragments use the same permutation).
 __device__ __forceinline__ void to_afrag(const float (&v)[4], int odd, float (&a)[4]) {
@@ -419,6 +435,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
     }
 
     constexpr bool kSectorProbe = TRAIN ? (SHINE_SECTOR_PROBE_TRAIN != 0) : (SHINE_SECTOR_PROBE_INFER != 0);
+    constexpr bool kSlotPrefetch = TRAIN && !kSectorProbe && (SHINE_SLOT_PREFETCH != 0) && (SHINE_CPASYNC_PREFETCH == 0);
     const bool poly = P.oct.poly_interp != 0;
     const int L = P.oct.num_levels;
     const float up = (TRAIN && P.d_loss) ? __ldg(P.d_loss) : 1.0f;
@@ -448,6 +465,30 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
 #pragma unroll
     for (int i = 1; i < LMAX; ++i)
         if (i < L && P.oct.lv[i].level != P.oct.lv[0].level - i) consecutive = false;
+
+    // staged one tile ahead (kSlotPrefetch): leaf Morton key and home-slot indices of this lane's levels; both 32-byte
+    // sectors of each home slot are pulled into L1 while the previous tile scatters, so the key and corner-id loads of the
+    // walk below hit L1 and only the row gather pays an L2 round trip
+    unsigned long long skey0 = 0ull;
+    int smine[LMAX / 2];
+#pragma unroll
+    for (int j = 0; j < LMAX / 2; ++j) smine[j] = -1;
+    auto stage_slots = [&](bool v, float sx, float sy, float sz) {
+        skey0 = v ? morton_of(sx, sy, sz, P.oct.lv[0].level) : 0ull;
+#pragma unroll
+        for (int j = 0; j < LMAX / 2; ++j) {
+            const int i = 2 * j + half;
+            smine[j] = -1;
+            if (i < L && v) {
+                const shine_level& lv = P.oct.lv[i];
+                const unsigned long long kq = consecutive ? (skey0 >> (3 * i)) : morton_of(sx, sy, sz, lv.level);
+                smine[j] = (int)(hash_key(kq) & (lv.hash_capacity - 1));
+                const char* sp = reinterpret_cast<const char*>(reinterpret_cast<const HashSlot*>(lv.hash_slots) + smine[j]);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(sp));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + 32));
+            }
+        }
+    };
 
 #if SHINE_CPASYNC_PREFETCH
     // software pipeline, depth 1: the next tile's coordinates / label / weight travel global -> shared memory with
@@ -504,6 +545,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         }
     };
     prefetch_inputs(warp_global);
+    if (kSlotPrefetch) stage_slots(nvalid, nx, ny, nz);   // first tile
 
     for (int tile = warp_global; tile < P.num_tiles; tile += warp_stride) {
         const int64_t base = (int64_t)tile * kTile;
@@ -567,12 +609,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                         const float wz = half ? b.tz : b.uz;
                         const float w0 = __fmul_rn(__fmul_rn(b.ux, b.uy), wz), w1 = __fmul_rn(__fmul_rn(b.ux, b.ty), wz);
                         const float w2 = __fmul_rn(__fmul_rn(b.tx, b.uy), wz), w3 = __fmul_rn(__fmul_rn(b.tx, b.ty), wz);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            float a = acc[q];
-                            a = fmaf(w0, r0[q], a); a = fmaf(w1, r1[q], a); a = fmaf(w2, r2[q], a); a = fmaf(w3, r3[q], a);
-                            acc[q] = a;
-                        }
+                        blend4(acc, r0, r1, r2, r3, w0, w1, w2, w3);
                     }
                 }
             }
@@ -590,7 +627,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         int slot[LMAX];
         {
             constexpr int LH = LMAX / 2;
-            const unsigned long long key0 = valid ? morton_of(x, y, z, P.oct.lv[0].level) : 0ull;
+            const unsigned long long key0 = kSlotPrefetch ? skey0 : (valid ? morton_of(x, y, z, P.oct.lv[0].level) : 0ull);
             unsigned long long kq[LH];
             uint4 kf[LH];          // home slot: {key lo, key hi, node, maxdisp}
             int mine[LH];
@@ -602,7 +639,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                     const shine_level& lv = P.oct.lv[i];
                     const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
                     kq[j] = consecutive ? (key0 >> (3 * i)) : morton_of(x, y, z, lv.level);
-                    mine[j] = (int)(hash_key(kq[j]) & (lv.hash_capacity - 1));
+                    mine[j] = kSlotPrefetch ? smine[j] : (int)(hash_key(kq[j]) & (lv.hash_capacity - 1));
                     kf[j] = __ldg(reinterpret_cast<const uint4*>(slots + mine[j]));
                 }
             }
@@ -661,12 +698,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                     const float wz = half ? b.tz : b.uz;
                     const float w0 = __fmul_rn(__fmul_rn(b.ux, b.uy), wz), w1 = __fmul_rn(__fmul_rn(b.ux, b.ty), wz);
                     const float w2 = __fmul_rn(__fmul_rn(b.tx, b.uy), wz), w3 = __fmul_rn(__fmul_rn(b.tx, b.ty), wz);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        float a = acc[q];
-                        a = fmaf(w0, r0[q], a); a = fmaf(w1, r1[q], a); a = fmaf(w2, r2[q], a); a = fmaf(w3, r3[q], a);
-                        acc[q] = a;
-                    }
+                    blend4(acc, r0, r1, r2, r3, w0, w1, w2, w3);
                 }
             }
 #pragma unroll
@@ -701,42 +733,53 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
             *reinterpret_cast<float4*>(stX + (g + 8 * odd) * kF + 4 * half) = make_float4(feat[0], feat[1], feat[2], feat[3]);
         float h1[4][4];
         uint32_t m1 = 0;   // ReLU mask of h1: bit 4j+r
+        {
+            uint2 bh[4], bl[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float bA = smem[SmemPlan::B1 + 8 * j + 2 * t], bB = smem[SmemPlan::B1 + 8 * j + 2 * t + 1];
-            float c[4] = {bA, bB, bA, bB};
-            const int off = (8 * j + g) * kF + 2 * t;
-            const uint2 bh = *reinterpret_cast<const uint2*>(smu + SmemPlan::W1 + off);
-            const uint2 bl = *reinterpret_cast<const uint2*>(smu + SmemPlan::W1 + kH * kF + off);
-            mma3<NTF>(c, ax, bh, bl);
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                h1[j][r] = fmaxf(c[r], 0.f);
-                if (TRAIN && c[r] > 0.f) m1 |= 1u << (4 * j + r);
+            for (int j = 0; j < 4; ++j) {
+                const float bA = smem[SmemPlan::B1 + 8 * j + 2 * t], bB = smem[SmemPlan::B1 + 8 * j + 2 * t + 1];
+                h1[j][0] = bA; h1[j][1] = bB; h1[j][2] = bA; h1[j][3] = bB;
+                const int off = (8 * j + g) * kF + 2 * t;
+                bh[j] = *reinterpret_cast<const uint2*>(smu + SmemPlan::W1 + off);
+                bl[j] = *reinterpret_cast<const uint2*>(smu + SmemPlan::W1 + kH * kF + off);
             }
-            if (DEC_GRAD) {
-                *reinterpret_cast<float2*>(stB + g * kWS + 8 * j + 2 * t) = make_float2(h1[j][0], h1[j][1]);
-                *reinterpret_cast<float2*>(stB + (g + 8) * kWS + 8 * j + 2 * t) = make_float2(h1[j][2], h1[j][3]);
+            mma3x4<NTF>(h1, ax, bh, bl);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if (TRAIN && h1[j][r] > 0.f) m1 |= 1u << (4 * j + r);
+                    h1[j][r] = fmaxf(h1[j][r], 0.f);
+                }
+                if (DEC_GRAD) {
+                    *reinterpret_cast<float2*>(stB + g * kWS + 8 * j + 2 * t) = make_float2(h1[j][0], h1[j][1]);
+                    *reinterpret_cast<float2*>(stB + (g + 8) * kWS + 8 * j + 2 * t) = make_float2(h1[j][2], h1[j][3]);
+                }
             }
         }
         float h2[4][4];
         {
-            AFrag<NTF> ah[4];
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk) ah[kk].set(h1[kk][0], h1[kk][2], h1[kk][1], h1[kk][3]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float bA = smem[SmemPlan::B2 + 8 * j + 2 * t], bB = smem[SmemPlan::B2 + 8 * j + 2 * t + 1];
-                float c[4] = {bA, bB, bA, bB};
+                h2[j][0] = bA; h2[j][1] = bB; h2[j][2] = bA; h2[j][3] = bB;
+            }
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
+            for (int kk = 0; kk < 4; ++kk) {
+                AFrag<NTF> a; a.set(h1[kk][0], h1[kk][2], h1[kk][1], h1[kk][3]);
+                uint2 bh[4], bl[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
                     const int off = (8 * j + g) * kWS + 8 * kk + 2 * t;
-                    const uint2 bh = *reinterpret_cast<const uint2*>(smu + SmemPlan::W2 + off);
-                    const uint2 bl = *reinterpret_cast<const uint2*>(smu + SmemPlan::W2 + kH * kWS + off);
-                    mma3<NTF>(c, ah[kk], bh, bl);
+                    bh[j] = *reinterpret_cast<const uint2*>(smu + SmemPlan::W2 + off);
+                    bl[j] = *reinterpret_cast<const uint2*>(smu + SmemPlan::W2 + kH * kWS + off);
                 }
+                mma3x4<NTF>(h2, a, bh, bl);
+            }
 #pragma unroll
-                for (int r = 0; r < 4; ++r) h2[j][r] = fmaxf(c[r], 0.f);
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int r = 0; r < 4; ++r) h2[j][r] = fmaxf(h2[j][r], 0.f);
             }
         }
         float w3a[4], w3b[4];
@@ -797,21 +840,24 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
 
         float dh1[4][4];
         {
-            AFrag<NTF> ad[4];
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) ad[kk].set(dh2[kk][0], dh2[kk][2], dh2[kk][1], dh2[kk][3]);
+            for (int j = 0; j < 4; ++j) { dh1[j][0] = dh1[j][1] = dh1[j][2] = dh1[j][3] = 0.f; }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                AFrag<NTF> a; a.set(dh2[kk][0], dh2[kk][2], dh2[kk][1], dh2[kk][3]);
+                uint2 bh[4], bl[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int off = (8 * j + g) * kWS + 8 * kk + 2 * t;
+                    bh[j] = *reinterpret_cast<const uint2*>(smu + SmemPlan::W2T + off);
+                    bl[j] = *reinterpret_cast<const uint2*>(smu + SmemPlan::W2T + kH * kWS + off);
+                }
+                mma3x4<NTF>(dh1, a, bh, bl);
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                float c[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                    const int off = (8 * j + g) * kWS + 8 * kk + 2 * t;
-                    const uint2 bh = *reinterpret_cast<const uint2*>(smu + SmemPlan::W2T + off);
-                    const uint2 bl = *reinterpret_cast<const uint2*>(smu + SmemPlan::W2T + kH * kWS + off);
-                    mma3<NTF>(c, ad[kk], bh, bl);
-                }
-#pragma unroll
-                for (int r = 0; r < 4; ++r) dh1[j][r] = ((m1 >> (4 * j + r)) & 1u) ? c[r] : 0.f;
+                for (int r = 0; r < 4; ++r) dh1[j][r] = ((m1 >> (4 * j + r)) & 1u) ? dh1[j][r] : 0.f;
                 if (DEC_GRAD) {
                     db1t[j][0] = dh1[j][0] + dh1[j][2]; db1t[j][1] = dh1[j][1] + dh1[j][3];
                     *reinterpret_cast<float2*>(stC + g * kWS + 8 * j + 2 * t) = make_float2(dh1[j][0], dh1[j][1]);
@@ -821,14 +867,21 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         }
         float dxc[4] = {0.f, 0.f, 0.f, 0.f};
         {
+            float dxo[4] = {0.f, 0.f, 0.f, 0.f};   // odd k-chunks: two interleaved accumulation chains instead of one
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) {
-                AFrag<NTF> a; a.set(dh1[kk][0], dh1[kk][2], dh1[kk][1], dh1[kk][3]);
+            for (int kk = 0; kk < 4; kk += 2) {
+                AFrag<NTF> a0, a1;
+                a0.set(dh1[kk][0], dh1[kk][2], dh1[kk][1], dh1[kk][3]);
+                a1.set(dh1[kk + 1][0], dh1[kk + 1][2], dh1[kk + 1][1], dh1[kk + 1][3]);
                 const int off = g * kWS + 8 * kk + 2 * t;
-                const uint2 bh = *reinterpret_cast<const uint2*>(smu + SmemPlan::W1T + off);
-                const uint2 bl = *reinterpret_cast<const uint2*>(smu + SmemPlan::W1T + kF * kWS + off);
-                mma3<NTF>(dxc, a, bh, bl);
+                const uint2 bh0 = *reinterpret_cast<const uint2*>(smu + SmemPlan::W1T + off);
+                const uint2 bl0 = *reinterpret_cast<const uint2*>(smu + SmemPlan::W1T + kF * kWS + off);
+                const uint2 bh1 = *reinterpret_cast<const uint2*>(smu + SmemPlan::W1T + off + 8);
+                const uint2 bl1 = *reinterpret_cast<const uint2*>(smu + SmemPlan::W1T + kF * kWS + off + 8);
+                mma3x2<NTF>(dxc, dxo, a0, a1, bh0, bl0, bh1, bl1);
             }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) dxc[r] += dxo[r];
         }
 
         // ---- backward: decoder weight grads (contraction over the tile's 16 points) -------------------
@@ -851,36 +904,36 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {
                     const float b0 = stB[(8 * ks + t) * kWS + 8 * nt + g], b1 = stB[(8 * ks + t + 4) * kWS + 8 * nt + g];
-                    split_fast(b0, bh[nt].x, bl[nt].x); split_fast(b1, bh[nt].y, bl[nt].y);
+                    split_fast2(b0, b1, bh[nt].x, bh[nt].y, bl[nt].x, bl[nt].y);
                 }
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
                     AFrag<NTF> a;
-                    a.set(stA[(8 * ks + t) * kWS + 16 * mt + g], stA[(8 * ks + t) * kWS + 16 * mt + g + 8],
+                    a.set_packed(stA[(8 * ks + t) * kWS + 16 * mt + g], stA[(8 * ks + t) * kWS + 16 * mt + g + 8],
                           stA[(8 * ks + t + 4) * kWS + 16 * mt + g], stA[(8 * ks + t + 4) * kWS + 16 * mt + g + 8]);
-#pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) mma3<NTF>(dW2[mt][nt], a, bh[nt], bl[nt]);
+                    mma3x4<NTF>(dW2[mt], a, bh, bl);
                 }
             }
             // dW1[n1][ch] += sum_rows dh1[row][n1] * feat[row][ch]
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
                 uint2 bh, bl;
-                split_fast(stX[(8 * ks + t) * kF + g], bh.x, bl.x);
-                split_fast(stX[(8 * ks + t + 4) * kF + g], bh.y, bl.y);
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    AFrag<NTF> a;
-                    a.set(stC[(8 * ks + t) * kWS + 16 * mt + g], stC[(8 * ks + t) * kWS + 16 * mt + g + 8],
-                          stC[(8 * ks + t + 4) * kWS + 16 * mt + g], stC[(8 * ks + t + 4) * kWS + 16 * mt + g + 8]);
-                    mma3<NTF>(dW1[mt], a, bh, bl);
-                }
+                split_fast2(stX[(8 * ks + t) * kF + g], stX[(8 * ks + t + 4) * kF + g], bh.x, bh.y, bl.x, bl.y);
+                AFrag<NTF> a0, a1;
+                a0.set_packed(stC[(8 * ks + t) * kWS + g], stC[(8 * ks + t) * kWS + g + 8],
+                              stC[(8 * ks + t + 4) * kWS + g], stC[(8 * ks + t + 4) * kWS + g + 8]);
+                a1.set_packed(stC[(8 * ks + t) * kWS + 16 + g], stC[(8 * ks + t) * kWS + 16 + g + 8],
+                              stC[(8 * ks + t + 4) * kWS + 16 + g], stC[(8 * ks + t + 4) * kWS + 16 + g + 8]);
+                mma3x2<NTF>(dW1[0], dW1[1], a0, a1, bh, bl, bh, bl);
             }
             __syncwarp();
             SHINE_ACC_STORE(tacc);
         }
 
         // ---- backward: scatter-add into the corner-feature tables (index_put_ accumulate) -------------
+#if !SHINE_CPASYNC_PREFETCH
+        if (kSlotPrefetch) stage_slots(nvalid, nx, ny, nz);   // next tile's hash + slot prefetch rides under the scatter
+#endif
         float dx[4];
         from_cfrag(dxc, odd, dx);
         float qk[kPark], qid[kIdPark];
@@ -906,10 +959,18 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                 float* gb = grad_base(lv, (uint32_t)tile, kF) + 4 * half;
                 // w_c = (X * Y) * Z in the reference's association; the four X*Y products are shared by the z pair
                 const float xy[4] = {__fmul_rn(b.ux, b.uy), __fmul_rn(b.ux, b.ty), __fmul_rn(b.tx, b.uy), __fmul_rn(b.tx, b.ty)};
+                const f2_t zz = f2_pack(b.uz, b.tz), dx01 = f2_pack(dx[0], dx[1]), dx23 = f2_pack(dx[2], dx[3]);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float w = __fmul_rn(xy[c >> 1], (c & 1) ? b.tz : b.uz);
-                    red_add_f4(gb + (int64_t)ids[c] * kF, w * dx[0], w * dx[1], w * dx[2], w * dx[3]);
+                for (int c = 0; c < 8; c += 2) {
+                    float w[2];
+                    f2_unpack(f2_mul(f2_pack(xy[c >> 1], xy[c >> 1]), zz), w[0], w[1]);    // (X*Y)*uz, (X*Y)*tz
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const f2_t wk = f2_pack(w[k], w[k]);
+                        float g0, g1, g2, g3;
+                        f2_unpack(f2_mul(wk, dx01), g0, g1); f2_unpack(f2_mul(wk, dx23), g2, g3);
+                        red_add_f4(gb + (int64_t)ids[c + k] * kF, g0, g1, g2, g3);
+                    }
                 }
             }
         }

@@ -274,9 +274,28 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 // activation split for 3xTF32: hi = x with the low 13 mantissa bits cleared (1 LOP), lo = x - hi (exact; the MMA
 // reads its top 19 bits).  x*w = hi*wh + hi*wl + lo*wh + O(2^-20 |x w|): same order as the cvt.rna split, one
 // instruction less per element.
+// The mask lives in constant memory on purpose: with a literal, ptxas knows that HMMA ignores the bits the AND clears, feeds
+// the unmasked value to the tensor core instead, and then re-assembles that operand quad with four MOVs before every use.
+__constant__ uint32_t g_tf32_mask = 0xFFFFE000u;
 __device__ __forceinline__ void split_fast(float x, uint32_t& hi, uint32_t& lo) {
-    hi = __float_as_uint(x) & 0xFFFFE000u;
+    hi = __float_as_uint(x) & g_tf32_mask;
     lo = __float_as_uint(x - __uint_as_float(hi));
+}
+// Packed fp32 pairs (sm_100a FFMA2 / FMUL2 / FADD2: two IEEE fp32 operations per lane per instruction; a scalar
+// operand broadcasts for free).  Same rounding as the scalar forms: results are bit-identical, the instruction count halves.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t f2_pack(float a, float b) { f2_t r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void f2_unpack(f2_t r, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) { f2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) { f2_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) { f2_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2_t f2_sub(f2_t a, f2_t b) { f2_t d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// split_fast of two values: 2 LOP3 + 1 FADD2
+__device__ __forceinline__ void split_fast2(float a, float b, uint32_t& ha, uint32_t& hb, uint32_t& la, uint32_t& lb) {
+    ha = __float_as_uint(a) & g_tf32_mask; hb = __float_as_uint(b) & g_tf32_mask;
+    float x, y;
+    f2_unpack(f2_sub(f2_pack(a, b), f2_pack(__uint_as_float(ha), __uint_as_float(hb))), x, y);
+    la = __float_as_uint(x); lb = __float_as_uint(y);
 }
 template <int NTF>
 struct AFrag {
@@ -289,6 +308,15 @@ struct AFrag {
             hi[0] = f2tf32(a0); hi[1] = f2tf32(a1); hi[2] = f2tf32(a2); hi[3] = f2tf32(a3);
         }
     }
+    // same, for operands that come straight from shared memory (no register-placement constraints): packed split
+    __device__ __forceinline__ void set_packed(float a0, float a1, float a2, float a3) {
+        if (NTF == 3) {
+            split_fast2(a0, a1, hi[0], hi[1], lo[0], lo[1]);
+            split_fast2(a2, a3, hi[2], hi[3], lo[2], lo[3]);
+        } else {
+            set(a0, a1, a2, a3);
+        }
+    }
 };
 template <int NTF>
 __device__ __forceinline__ void mma3(float (&d)[4], const AFrag<NTF>& a, uint2 bh, uint2 bl) {
@@ -297,6 +325,30 @@ __device__ __forceinline__ void mma3(float (&d)[4], const AFrag<NTF>& a, uint2 b
         mma_tf32(d, a.hi, bl.x, bl.y);
     }
     mma_tf32(d, a.hi, bh.x, bh.y);
+}
+
+// the same three products for four independent accumulators sharing one A fragment, issued term by term: consecutive
+// HMMAs never depend on each other (the per-accumulator order, hence the result, is that of four mma3 calls)
+template <int NTF>
+__device__ __forceinline__ void mma3x4(float (&d)[4][4], const AFrag<NTF>& a, const uint2 (&bh)[4], const uint2 (&bl)[4]) {
+    if (NTF == 3) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_tf32(d[j], a.lo, bh[j].x, bh[j].y);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_tf32(d[j], a.hi, bl[j].x, bl[j].y);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) mma_tf32(d[j], a.hi, bh[j].x, bh[j].y);
+}
+// two accumulators, two A fragments, one B fragment pair each
+template <int NTF>
+__device__ __forceinline__ void mma3x2(float (&d0)[4], float (&d1)[4], const AFrag<NTF>& a0, const AFrag<NTF>& a1,
+                                       uint2 bh0, uint2 bl0, uint2 bh1, uint2 bl1) {
+    if (NTF == 3) {
+        mma_tf32(d0, a0.lo, bh0.x, bh0.y); mma_tf32(d1, a1.lo, bh1.x, bh1.y);
+        mma_tf32(d0, a0.hi, bl0.x, bl0.y); mma_tf32(d1, a1.hi, bl1.x, bl1.y);
+    }
+    mma_tf32(d0, a0.hi, bh0.x, bh0.y); mma_tf32(d1, a1.hi, bh1.x, bh1.y);
 }
 
 // ------------------------------------------------------------------------------------------------------
