@@ -41,7 +41,7 @@
 #define SHINE_GATHER_GROUP 2  // levels whose first-probe sectors are in flight together (register pressure vs parallelism)
 #endif
 #ifndef SHINE_SLOT_PREFETCH
-#define SHINE_SLOT_PREFETCH 1  // training kernel: hash + L1 prefetch of the NEXT tile's home slots before this tile's scatter
+#define SHINE_SLOT_PREFETCH 0  // training kernel: hash + L1 prefetch of the NEXT tile's home slots before this tile's scatter
 #endif
 #ifndef SHINE_TRAIN_MINB
 #define SHINE_TRAIN_MINB 2    // min resident blocks/SM of the training kernel (register cap 65536/(256*MINB))
@@ -184,12 +184,7 @@ __global__ void __launch_bounds__(256) query_fwd8_kernel(const __grid_constant__
         const float wz = half ? b.tz : b.uz;
         const float w0 = __fmul_rn(__fmul_rn(b.ux, b.uy), wz), w1 = __fmul_rn(__fmul_rn(b.ux, b.ty), wz);
         const float w2 = __fmul_rn(__fmul_rn(b.tx, b.uy), wz), w3 = __fmul_rn(__fmul_rn(b.tx, b.ty), wz);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            float a = acc[q];
-            a = fmaf(w0, r0[q], a); a = fmaf(w1, r1[q], a); a = fmaf(w2, r2[q], a); a = fmaf(w3, r3[q], a);
-            acc[q] = a;
-        }
+        blend4(acc, r0, r1, r2, r3, w0, w1, w2, w3);
     }
     float4 o;
     {
@@ -294,19 +289,6 @@ __global__ void __launch_bounds__(256) query_tangent_kernel(const __grid_constan
         if (valid && part == 0) { out[3 * p] = g3[0]; out[3 * p + 1] = g3[1]; out[3 * p + 2] = g3[2]; }
     } else if (MODE == 1) {
         if (valid) *reinterpret_cast<float4*>(out + p * F + 4 * part) = acc;
-    }
-}
-
-// acc[q] = fma(w3, r3[q], fma(w2, r2[q], fma(w1, r1[q], fma(w0, r0[q], acc[q])))) for the 8 channels, two per FFMA2
-__device__ __forceinline__ void blend4(float (&acc)[8], const float (&r0)[8], const float (&r1)[8], const float (&r2)[8],
-                                       const float (&r3)[8], float w0, float w1, float w2, float w3) {
-    const f2_t p0 = f2_pack(w0, w0), p1 = f2_pack(w1, w1), p2 = f2_pack(w2, w2), p3 = f2_pack(w3, w3);
-#pragma unroll
-    for (int q = 0; q < 8; q += 2) {
-        f2_t a = f2_pack(acc[q], acc[q + 1]);
-        a = f2_fma(p0, f2_pack(r0[q], r0[q + 1]), a); a = f2_fma(p1, f2_pack(r1[q], r1[q + 1]), a);
-        a = f2_fma(p2, f2_pack(r2[q], r2[q + 1]), a); a = f2_fma(p3, f2_pack(r3[q], r3[q + 1]), a);
-        f2_unpack(a, acc[q], acc[q + 1]);
     }
 }
 
@@ -1178,12 +1160,7 @@ __global__ void __launch_bounds__(128, 5) sdf_infer_tc_kernel(const __grid_const
                         const float wz = half ? b.tz : b.uz;
                         const float w0 = __fmul_rn(__fmul_rn(b.ux, b.uy), wz), w1 = __fmul_rn(__fmul_rn(b.ux, b.ty), wz);
                         const float w2 = __fmul_rn(__fmul_rn(b.tx, b.uy), wz), w3 = __fmul_rn(__fmul_rn(b.tx, b.ty), wz);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            float a = acc[q];
-                            a = fmaf(w0, q0[q], a); a = fmaf(w1, q1[q], a); a = fmaf(w2, q2[q], a); a = fmaf(w3, q3[q], a);
-                            acc[q] = a;
-                        }
+                        blend4(acc, q0, q1, q2, q3, w0, w1, w2, w3);
                     }
                 }
             }

@@ -327,6 +327,19 @@ __device__ __forceinline__ void mma3(float (&d)[4], const AFrag<NTF>& a, uint2 b
     mma_tf32(d, a.hi, bh.x, bh.y);
 }
 
+// acc[q] = fma(w3, r3[q], fma(w2, r2[q], fma(w1, r1[q], fma(w0, r0[q], acc[q])))) for the 8 channels, two per FFMA2
+__device__ __forceinline__ void blend4(float (&acc)[8], const float (&r0)[8], const float (&r1)[8], const float (&r2)[8],
+                                       const float (&r3)[8], float w0, float w1, float w2, float w3) {
+    const f2_t p0 = f2_pack(w0, w0), p1 = f2_pack(w1, w1), p2 = f2_pack(w2, w2), p3 = f2_pack(w3, w3);
+#pragma unroll
+    for (int q = 0; q < 8; q += 2) {
+        f2_t a = f2_pack(acc[q], acc[q + 1]);
+        a = f2_fma(p0, f2_pack(r0[q], r0[q + 1]), a); a = f2_fma(p1, f2_pack(r1[q], r1[q + 1]), a);
+        a = f2_fma(p2, f2_pack(r2[q], r2[q + 1]), a); a = f2_fma(p3, f2_pack(r3[q], r3[q + 1]), a);
+        f2_unpack(a, acc[q], acc[q + 1]);
+    }
+}
+
 // the same three products for four independent accumulators sharing one A fragment, issued term by term: consecutive
 // HMMAs never depend on each other (the per-accumulator order, hence the result, is that of four mma3 calls)
 template <int NTF>

@@ -276,27 +276,25 @@ __global__ void __launch_bounds__(kET, 2) sdf_eikonal_kernel(const __grid_consta
                 // dp of points 8ks+t / 8ks+t+4 as an extra B column (n = 0): the bias gradients ride on the same MMAs
                 const float d0 = __shfl_sync(kFull, dp, 8 * ks + t), d1 = __shfl_sync(kFull, dp, 8 * ks + t + 4);
                 uint2 bdh, bdl;
-                split_fast(g == 0 ? d0 : 0.f, bdh.x, bdl.x); split_fast(g == 0 ? d1 : 0.f, bdh.y, bdl.y);
+                split_fast2(g == 0 ? d0 : 0.f, g == 0 ? d1 : 0.f, bdh.x, bdh.y, bdl.x, bdl.y);
                 uint2 bh[4], bl[4];
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) {       // B[k = point][n = k1] = u
-                    split_fast(tU[(8 * nt + g) * kTS + 8 * ks + t], bh[nt].x, bl[nt].x);
-                    split_fast(tU[(8 * nt + g) * kTS + 8 * ks + t + 4], bh[nt].y, bl[nt].y);
+                    split_fast2(tU[(8 * nt + g) * kTS + 8 * ks + t], tU[(8 * nt + g) * kTS + 8 * ks + t + 4], bh[nt].x, bh[nt].y,
+                                bl[nt].x, bl[nt].y);
                 }
                 uint2 vh, vl;
-                split_fast(tV[g * kTS + 8 * ks + t], vh.x, vl.x); split_fast(tV[g * kTS + 8 * ks + t + 4], vh.y, vl.y);
+                split_fast2(tV[g * kTS + 8 * ks + t], tV[g * kTS + 8 * ks + t + 4], vh.x, vh.y, vl.x, vl.y);
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
                     AFrag<3> a;       // a2^T: rows = n2, cols = points
-                    a.set(tA2[(16 * mt + g) * kTS + 8 * ks + t], tA2[(16 * mt + g + 8) * kTS + 8 * ks + t],
-                          tA2[(16 * mt + g) * kTS + 8 * ks + t + 4], tA2[(16 * mt + g + 8) * kTS + 8 * ks + t + 4]);
-#pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) mma3<3>(dW2[mt][nt], a, bh[nt], bl[nt]);
-                    mma3<3>(db2x[mt], a, bdh, bdl);
+                    a.set_packed(tA2[(16 * mt + g) * kTS + 8 * ks + t], tA2[(16 * mt + g + 8) * kTS + 8 * ks + t],
+                                 tA2[(16 * mt + g) * kTS + 8 * ks + t + 4], tA2[(16 * mt + g + 8) * kTS + 8 * ks + t + 4]);
                     AFrag<3> c;       // a1^T: rows = n1, cols = points
-                    c.set(tA1[(16 * mt + g) * kTS + 8 * ks + t], tA1[(16 * mt + g + 8) * kTS + 8 * ks + t],
-                          tA1[(16 * mt + g) * kTS + 8 * ks + t + 4], tA1[(16 * mt + g + 8) * kTS + 8 * ks + t + 4]);
-                    mma3<3>(dW1[mt], c, vh, vl);
+                    c.set_packed(tA1[(16 * mt + g) * kTS + 8 * ks + t], tA1[(16 * mt + g + 8) * kTS + 8 * ks + t],
+                                 tA1[(16 * mt + g) * kTS + 8 * ks + t + 4], tA1[(16 * mt + g + 8) * kTS + 8 * ks + t + 4]);
+                    mma3x4<3>(dW2[mt], a, bh, bl);                       // term-major: no back-to-back dependent HMMAs
+                    mma3x2<3>(db2x[mt], dW1[mt], a, c, bdh, bdl, vh, vl);
                     mma3<3>(db1x[mt], c, bdh, bdl);
                 }
             }

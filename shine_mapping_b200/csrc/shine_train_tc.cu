@@ -238,12 +238,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) sdf_train_tc_kernel(const __gri
                     const float wz = half ? b.tz : b.uz;
                     const float w0 = __fmul_rn(__fmul_rn(b.ux, b.uy), wz), w1 = __fmul_rn(__fmul_rn(b.ux, b.ty), wz);
                     const float w2 = __fmul_rn(__fmul_rn(b.tx, b.uy), wz), w3 = __fmul_rn(__fmul_rn(b.tx, b.ty), wz);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        float a = acc[q];
-                        a = fmaf(w0, r0[q], a); a = fmaf(w1, r1[q], a); a = fmaf(w2, r2[q], a); a = fmaf(w3, r3[q], a);
-                        acc[q] = a;
-                    }
+                    blend4(acc, r0, r1, r2, r3, w0, w1, w2, w3);
                 }
             }
             tmem_st16(tpark, pk); tmem_st16(tpark + 16, idp);

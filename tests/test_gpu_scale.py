@@ -7,6 +7,8 @@
 * probe chains forced by building the node tables at load factor ~1 (SHINE_HASH_SLOTS_PER_NODE = 1).
 Tolerances: tests/parity_utils.py (indices exact, loss 2e-5, gradients 2e-4 of the level maximum).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -164,8 +166,9 @@ def test_cuda_update_matches_oracle_tables_frame_by_frame():
             torch.cuda.synchronize()
         ev = [e for e in prof.key_averages() if e.device_type == torch.autograd.DeviceType.CUDA]
         names = [e.key for e in ev]
-        assert not any("unique" in k.lower() for k in names), names
-        assert any("frame_nodes_kernel" in k for k in names) and any("fill_nodes_kernel" in k for k in names), names
+        if names or os.environ.get("SHINE_UNDER_SANITIZER") != "1":   # CUPTI sees nothing under compute-sanitizer
+            assert not any("unique" in k.lower() for k in names), names
+            assert any("frame_nodes_kernel" in k for k in names) and any("fill_nodes_kernel" in k for k in names), names
         launches.append(sum(e.count for e in ev))
         o.update(surf.cpu())
         for lvl in range(octree.free_level_num, octree.max_level + 1):
@@ -176,6 +179,7 @@ def test_cuda_update_matches_oracle_tables_frame_by_frame():
     print("update() device launches per frame (kernels + memsets + copies):", launches,
           "rows:", [int(p.shape[0]) for p in octree.hier_features])
     assert max(launches[1:]) <= 80, launches
+    assert min(launches) > 0 or os.environ.get("SHINE_UNDER_SANITIZER") == "1", launches
     # queries on the incrementally built tables agree with the oracle
     c = frames[-1][0][:5000]
     for a, b in zip(octree.get_indices(c), o.get_indices(c.cpu())):
