@@ -45,6 +45,11 @@ extern "C" {
 #define SHINE_FLAG_TCGEN05 8u         /* shine_sdf_infer / shine_sdf_bce_step: decoder on tcgen05.mma with TMEM accumulators
                                          (128-point tiles, warp-specialised gather / epilogue warps) instead of
                                          warp-level mma.sync                                                  */
+#define SHINE_FLAG_MORTON_ORDERED 16u  /* shine_sdf_bce_step: the batch is in Morton order of its coordinates (the order the
+                                         Morton-sorted sample pool hands batches out in).  A hint, never a requirement:
+                                         neighbouring points then share nodes, and the step sums the gradients of each run of
+                                         equal node on the tensor cores before ONE red per corner row (results equal up to
+                                         fp32 summation order); on an unordered batch the flag only costs time           */
 
 /* One featured level of the FeatureOctree (model/feature_octree.py:46-63). */
 typedef struct shine_level {

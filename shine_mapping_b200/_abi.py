@@ -21,6 +21,7 @@ FLAG_REDUCTION_SUM = 1
 FLAG_WEIGHTED = 2
 FLAG_TF32X1 = 4
 FLAG_TCGEN05 = 8
+FLAG_MORTON_ORDERED = 16
 
 
 class ShineLevel(C.Structure):

@@ -97,7 +97,7 @@ class _GraphedIteration:
         if self.trainer.config.ekional_loss_on:
             self.trainer.forward_backward_eikonal(coord, sdf_label, weight)
         else:
-            self.trainer.forward_backward(coord, sdf_label, weight)
+            self.trainer.forward_backward(coord, sdf_label, weight, morton_ordered=getattr(self.pool, "ordered", False))
         self.trainer.optimizer_step(zero_grad=True, device_step=True)
 
     def run(self):
@@ -149,7 +149,8 @@ def run_shine_mapping_batch(config: SHINEConfig, octree: FeatureOctree, decoder:
             trainer.optimizer_step(zero_grad=True)
         else:
             coord, sdf_label, weight = pool.get_batch(config.bs)                       # shine_batch.py:115
-            trainer.forward_backward(coord, sdf_label, weight, n_norm=config.bs * world)   # :123-209
+            trainer.forward_backward(coord, sdf_label, weight, n_norm=config.bs * world,   # :123-209
+                                     morton_ordered=getattr(pool, "ordered", False))
             trainer.all_reduce_grads()
             trainer.optimizer_step(zero_grad=True)                                      # :208-210
         if it == 0 or it == iters - 1 or (log_every and it % log_every == 0):

@@ -43,6 +43,9 @@
 #ifndef SHINE_SLOT_PREFETCH
 #define SHINE_SLOT_PREFETCH 0  // training kernel: hash + L1 prefetch of the NEXT tile's home slots before this tile's scatter
 #endif
+#ifndef SHINE_EXPERIMENT_NO_RED
+#define SHINE_EXPERIMENT_NO_RED 0
+#endif
 #ifndef SHINE_TRAIN_MINB
 #define SHINE_TRAIN_MINB 2    // min resident blocks/SM of the training kernel (register cap 65536/(256*MINB))
 #endif
@@ -351,10 +354,133 @@ struct SmemPlan {
     static constexpr int kPrePerWarp = 5 * kTile;
     static constexpr int STAGE = PRE + 8 * kPrePerWarp;   // per-warp staging: 3 x [16][kWS] + [16][8]
     static constexpr int kStagePerWarp = 3 * kTile * kWS + kTile * kF;   // dh2 | h1 | dh1 | feat tiles
+    // GROUPED only, after the staging area: per warp and level [tx | ty | tz | node slot] x 16 points, and (frozen decoder:
+    // no staging area to borrow from) the [16][8] dL/dfeature tile
+    static constexpr int kGroupPerLevel = 4 * kTile;
 };
 
-template <int NTF, bool TRAIN, bool DEC_GRAD, int LMAX>
+// ---- voxel-grouped scatter (GROUPED kernels: batches in Morton order) ---------------------------------------------
+// In a Morton-ordered batch the 16 points of a tile fall into a few runs of equal node per level.  The per-run gradient
+// of the node's 8 corner rows is a small contraction over the run's points,
+//     G[corner][channel] = sum_p w_corner(p) * dL/dfeature(p)[channel]          (8 x npts) x (npts x 8),
+// so it runs on the tensor cores (m16n8k8, 3xTF32, rows 0-7 = corners of one run, rows 8-15 = corners of the next) and
+// each run issues ONE 8-byte red per lane (8 rows x 32 B per instruction) instead of one 16-byte red per point and corner:
+// the same-address atomics that serialise in L2 when neighbouring points share a voxel disappear.  Correct for any order
+// (a level with more than kMaxGroupedRuns runs takes the per-point path).
+constexpr int kMaxGroupedRuns = 6;
+
+__device__ __forceinline__ void red_add_f2(float* p, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
+}
+// permuted point index of the per-level tables: points t, t+4, t+8, t+12 are contiguous (one LDS.128 per field)
+__device__ __forceinline__ int group_slot(int p) { return 4 * (p & 3) + (p >> 2); }
+
+template <int LMAX>
+__device__ __forceinline__ void grouped_scatter(const StepParams& P, int L, int tile, const float* __restrict__ pt,
+                                                float* __restrict__ dtile, const float (&dxc)[4], int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    // dL/dfeature tile: C fragment (rows = points g, g+8; cols = channels 2t, 2t+1) -> [point][channel]
+    *reinterpret_cast<float2*>(dtile + g * kF + 2 * t) = make_float2(dxc[0], dxc[1]);
+    *reinterpret_cast<float2*>(dtile + (g + 8) * kF + 2 * t) = make_float2(dxc[2], dxc[3]);
+    __syncwarp();
+    // B fragments (k = point, n = channel g): chunk c covers points 8c .. 8c+7
+    uint2 bh[2], bl[2];
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+        split_fast2(dtile[(8 * c + t) * kF + g], dtile[(8 * c + t + 4) * kF + g], bh[c].x, bh[c].y, bl[c].x, bl[c].y);
+    // this lane's row of the A operand is corner g = (x bit 2, y bit 1, z bit 0): X = bit ? t : 1 - t as one FMA
+    const float sx = (g & 4) ? 1.f : -1.f, ox = (g & 4) ? 0.f : 1.f;
+    const float sy = (g & 2) ? 1.f : -1.f, oy = (g & 2) ? 0.f : 1.f;
+    const float sz = (g & 1) ? 1.f : -1.f, oz = (g & 1) ? 0.f : 1.f;
+    const int id_off = 8 * (g & 1) + 4 + (g >> 1);            // word of corner g's row index inside a 16-word HashSlot
+    const int own = group_slot(lane & 15), prev = group_slot((lane + 15) & 15);
+#pragma unroll
+    for (int i = 0; i < LMAX; ++i) {
+        if (i >= L) break;
+        const float* lt = pt + i * SmemPlan::kGroupPerLevel;
+        // run structure of the level: point p starts a run when its node differs from point p-1's (lanes 0..15 <-> points)
+        const int v_own = __float_as_int(lt[48 + own]);
+        const int v_prev = __float_as_int(lt[48 + prev]);
+        const uint32_t bmask = __ballot_sync(kFull, (lane & 15) == 0 || v_own != v_prev) & 0xFFFFu;
+        const uint32_t anyhit = __ballot_sync(kFull, v_own >= 0);
+        if (anyhit == 0) continue;
+        const shine_level& lv = P.oct.lv[i];
+        const int32_t* slot_words = reinterpret_cast<const int32_t*>(lv.hash_slots);
+        float* gb = grad_base(lv, (uint32_t)tile, kF);
+        const int nruns = __popc(bmask);
+        if (nruns > kMaxGroupedRuns) {
+            // scattered tile (batch not in Morton order): per-point reds, this lane = channels 4*half.. of point g + 8*odd
+            const int odd = t & 1, half = t >> 1, mp = group_slot(g + 8 * odd);
+            const int v = __float_as_int(lt[48 + mp]);
+            if (v >= 0) {
+                const float tx = lt[mp], ty = lt[16 + mp], tz = lt[32 + mp];
+                const float ux = __fsub_rn(1.0f, tx), uy = __fsub_rn(1.0f, ty), uz = __fsub_rn(1.0f, tz);
+                const int4 e = ldg_i4(slot_words + 16 * (int64_t)v + 4), o = ldg_i4(slot_words + 16 * (int64_t)v + 12);
+                const int ids[8] = {e.x, o.x, e.y, o.y, e.z, o.z, e.w, o.w};
+                const float4 d = *reinterpret_cast<const float4*>(dtile + (g + 8 * odd) * kF + 4 * half);
+                const float xy[4] = {__fmul_rn(ux, uy), __fmul_rn(ux, ty), __fmul_rn(tx, uy), __fmul_rn(tx, ty)};
+                const f2_t zz = f2_pack(uz, tz), d01 = f2_pack(d.x, d.y), d23 = f2_pack(d.z, d.w);
+#pragma unroll
+                for (int c = 0; c < 8; c += 2) {
+                    float w[2];
+                    f2_unpack(f2_mul(f2_pack(xy[c >> 1], xy[c >> 1]), zz), w[0], w[1]);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const f2_t wk = f2_pack(w[k], w[k]);
+                        float g0, g1, g2, g3;
+                        f2_unpack(f2_mul(wk, d01), g0, g1); f2_unpack(f2_mul(wk, d23), g2, g3);
+                        red_add_f4(gb + (int64_t)ids[c + k] * kF + 4 * half, g0, g1, g2, g3);
+                    }
+                }
+            }
+            continue;
+        }
+        // weights of corner g for points t, t+4, t+8, t+12 (reference association (X*Y)*Z)
+        const float4 tx4 = *reinterpret_cast<const float4*>(lt + 4 * t);
+        const float4 ty4 = *reinterpret_cast<const float4*>(lt + 16 + 4 * t);
+        const float4 tz4 = *reinterpret_cast<const float4*>(lt + 32 + 4 * t);
+        float w[4];
+        {
+            const f2_t s_x = f2_pack(sx, sx), o_x = f2_pack(ox, ox), s_y = f2_pack(sy, sy), o_y = f2_pack(oy, oy);
+            const f2_t s_z = f2_pack(sz, sz), o_z = f2_pack(oz, oz);
+            const f2_t X01 = f2_fma(f2_pack(tx4.x, tx4.y), s_x, o_x), X23 = f2_fma(f2_pack(tx4.z, tx4.w), s_x, o_x);
+            const f2_t Y01 = f2_fma(f2_pack(ty4.x, ty4.y), s_y, o_y), Y23 = f2_fma(f2_pack(ty4.z, ty4.w), s_y, o_y);
+            const f2_t Z01 = f2_fma(f2_pack(tz4.x, tz4.y), s_z, o_z), Z23 = f2_fma(f2_pack(tz4.z, tz4.w), s_z, o_z);
+            f2_unpack(f2_mul(f2_mul(X01, Y01), Z01), w[0], w[1]);
+            f2_unpack(f2_mul(f2_mul(X23, Y23), Z23), w[2], w[3]);
+        }
+        // run index of those four points
+        int rid[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rid[q] = __popc(bmask & ((2u << (t + 4 * q)) - 1u)) - 1;
+        uint32_t rem = bmask;
+        for (int r = 0; r < nruns; r += 2) {
+            const int p1 = __ffs(rem) - 1; rem &= rem - 1;
+            const int p2 = rem ? __ffs(rem) - 1 : p1; rem &= rem - 1;     // odd run count: the last pass has one run only
+            const int v1 = __shfl_sync(kFull, v_own, p1);
+            const int v2 = (r + 1 < nruns) ? __shfl_sync(kFull, v_own, p2) : -1;
+            if (v1 < 0 && v2 < 0) continue;                              // runs of misses
+            AFrag<3> a0, a1;     // rows g: run r, rows g + 8: run r + 1; k = points of chunk 0 / chunk 1
+            a0.set(rid[0] == r ? w[0] : 0.f, rid[0] == r + 1 ? w[0] : 0.f, rid[1] == r ? w[1] : 0.f, rid[1] == r + 1 ? w[1] : 0.f);
+            a1.set(rid[2] == r ? w[2] : 0.f, rid[2] == r + 1 ? w[2] : 0.f, rid[3] == r ? w[3] : 0.f, rid[3] == r + 1 ? w[3] : 0.f);
+            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};
+            mma3x2<3>(c0, c1, a0, a1, bh[0], bl[0], bh[1], bl[1]);
+            if (v1 >= 0) {
+                const int row = __ldg(slot_words + 16 * (int64_t)v1 + id_off);
+                red_add_f2(gb + (int64_t)row * kF + 2 * t, c0[0] + c1[0], c0[1] + c1[1]);
+            }
+            if (v2 >= 0) {
+                const int row = __ldg(slot_words + 16 * (int64_t)v2 + id_off);
+                red_add_f2(gb + (int64_t)row * kF + 2 * t, c0[2] + c1[2], c0[3] + c1[3]);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <int NTF, bool TRAIN, bool DEC_GRAD, int LMAX, bool GROUPED = false>
 __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MINB) sdf_fused_kernel(const __grid_constant__ StepParams P) {
+    static_assert(!GROUPED || TRAIN, "the grouped scatter belongs to the training kernels");
     extern __shared__ __align__(16) float smem[];
     uint32_t* smu = reinterpret_cast<uint32_t*>(smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -437,6 +563,10 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
     float* stB = stage + kTile * kWS;         // [16][kWS]
     float* stC = stage + 2 * kTile * kWS;     // [16][kWS]
     float* stX = stage + 3 * kTile * kWS;     // [16][8]
+    // GROUPED: per-warp level tables behind the staging area; the dL/dfeature tile borrows stX (dead after the wgrad section)
+    float* gpt = smem + SmemPlan::STAGE + (DEC_GRAD ? 8 * SmemPlan::kStagePerWarp : 0) +
+                 warp * (LMAX * SmemPlan::kGroupPerLevel + (DEC_GRAD ? 0 : kTile * kF));
+    float* gdx = DEC_GRAD ? stX : gpt + LMAX * SmemPlan::kGroupPerLevel;
 
     const int warp_global = blockIdx.x * kWarps + warp;
     const int warp_stride = gridDim.x * kWarps;
@@ -663,6 +793,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
             for (int i = 0; i < kIdPark; ++i) idp[i] = __int_as_float(-1);
 #pragma unroll
             for (int i = 0; i < LMAX; ++i) {
+                if (GROUPED && i < L && half) gpt[i * SmemPlan::kGroupPerLevel + 48 + group_slot(g + 8 * odd)] = __int_as_float(slot[i]);
                 if (i < L && slot[i] >= 0) {
                     const shine_level& lv = P.oct.lv[i];
                     const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
@@ -677,6 +808,10 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                     ldg_row8(lv.features + (int64_t)id4.w * kF, r3);
                     Blend b; b.init(x, y, z, lv.level, poly);
                     pk[3 * i] = b.tx; pk[3 * i + 1] = b.ty; pk[3 * i + 2] = b.tz;
+                    if (GROUPED) {
+                        float* lt = gpt + i * SmemPlan::kGroupPerLevel + group_slot(g + 8 * odd);
+                        if (half) lt[32] = b.tz; else { lt[0] = b.tx; lt[16] = b.ty; }
+                    }
                     const float wz = half ? b.tz : b.uz;
                     const float w0 = __fmul_rn(__fmul_rn(b.ux, b.uy), wz), w1 = __fmul_rn(__fmul_rn(b.ux, b.ty), wz);
                     const float w2 = __fmul_rn(__fmul_rn(b.tx, b.uy), wz), w3 = __fmul_rn(__fmul_rn(b.tx, b.ty), wz);
@@ -691,7 +826,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
             }
         }
         }
-        if (TRAIN) {
+        if (TRAIN && !GROUPED) {
             if (kPark == 16) tmem_st16(tpark, pk); else tmem_st32(tpark, pk);
             if (kIdPark == 16) tmem_st16(tpark + kPark, idp); else tmem_st32(tpark + kPark, idp);
             tmem_wait_st();
@@ -916,6 +1051,11 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
 #if !SHINE_CPASYNC_PREFETCH
         if (kSlotPrefetch) stage_slots(nvalid, nx, ny, nz);   // next tile's hash + slot prefetch rides under the scatter
 #endif
+        if constexpr (GROUPED) {
+            static_assert(!GROUPED || !kSectorProbe, "the grouped scatter reads the node slots of the level-split walk");
+            grouped_scatter<LMAX>(P, L, tile, gpt, gdx, dxc, lane);
+            continue;
+        }
         float dx[4];
         from_cfrag(dxc, odd, dx);
         float qk[kPark], qid[kIdPark];
@@ -951,6 +1091,9 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                         const f2_t wk = f2_pack(w[k], w[k]);
                         float g0, g1, g2, g3;
                         f2_unpack(f2_mul(wk, dx01), g0, g1); f2_unpack(f2_mul(wk, dx23), g2, g3);
+#if SHINE_EXPERIMENT_NO_RED      // bound experiment: what the step costs without the scatter's memory traffic
+                        if (P.sigma == -12345.f)
+#endif
                         red_add_f4(gb + (int64_t)ids[c + k] * kF, g0, g1, g2, g3);
                     }
                 }
@@ -1363,10 +1506,11 @@ int check_decoder(const shine_decoder* d, const shine_octree* o) {
     return SHINE_OK;
 }
 
-template <int NTF, bool TRAIN, bool DEC_GRAD, int LMAX>
+template <int NTF, bool TRAIN, bool DEC_GRAD, int LMAX, bool GROUPED = false>
 int launch_fused_t(const StepParams& P, cudaStream_t st) {
-    auto kern = sdf_fused_kernel<NTF, TRAIN, DEC_GRAD, LMAX>;
-    const int smem_floats = SmemPlan::STAGE + (DEC_GRAD ? 8 * SmemPlan::kStagePerWarp : 0);
+    auto kern = sdf_fused_kernel<NTF, TRAIN, DEC_GRAD, LMAX, GROUPED>;
+    const int smem_floats = SmemPlan::STAGE + (DEC_GRAD ? 8 * SmemPlan::kStagePerWarp : 0) +
+                            (GROUPED ? 8 * (LMAX * SmemPlan::kGroupPerLevel + (DEC_GRAD ? 0 : kTile * kF)) : 0);
     const size_t smem_bytes = (size_t)smem_floats * sizeof(float);
     static int per_sm_by_dev[kMaxDevices] = {0};   // per template instantiation AND per device: the >48 KB dynamic
     int& per_sm_cached = per_sm_by_dev[current_device()];   // shared-memory opt-in is a per-device function attribute
@@ -1404,6 +1548,9 @@ template <bool TRAIN, bool DEC_GRAD>
 int launch_fused(const StepParams& P, uint32_t flags, cudaStream_t st) {
     const bool x1 = (flags & SHINE_FLAG_TF32X1) != 0;
     const bool small = P.oct.num_levels <= 4;
+    if constexpr (TRAIN) {      // Morton-ordered batches: voxel-grouped scatter (3xTF32, up to 4 levels; else the general kernel)
+        if ((flags & SHINE_FLAG_MORTON_ORDERED) && !x1 && small) return launch_fused_t<3, TRAIN, DEC_GRAD, 4, true>(P, st);
+    }
     if (x1) return small ? launch_fused_t<1, TRAIN, DEC_GRAD, 4>(P, st) : launch_fused_t<1, TRAIN, DEC_GRAD, 8>(P, st);
     return small ? launch_fused_t<3, TRAIN, DEC_GRAD, 4>(P, st) : launch_fused_t<3, TRAIN, DEC_GRAD, 8>(P, st);
 }

@@ -18,7 +18,8 @@ from .decoder import Decoder
 from .feature_octree import FeatureOctree
 
 
-def _flags(weighted: bool, reduction: str, tf32x1: bool) -> int:
+def _flags(weighted: bool, reduction: str, extra) -> int:
+    """extra: True / False (plain-TF32 decoder) or an int of further SHINE_FLAG_* bits (TF32X1, MORTON_ORDERED)."""
     if reduction not in ("mean", "sum"):
         raise ValueError(f"loss_reduction must be 'mean' or 'sum', got {reduction!r}")
     f = 0
@@ -26,8 +27,10 @@ def _flags(weighted: bool, reduction: str, tf32x1: bool) -> int:
         f |= _abi.FLAG_REDUCTION_SUM
     if weighted:
         f |= _abi.FLAG_WEIGHTED
-    if tf32x1:
+    if extra is True:
         f |= _abi.FLAG_TF32X1
+    elif extra:
+        f |= int(extra)
     return f
 
 
@@ -112,11 +115,13 @@ class _SdfBce(torch.autograd.Function):
 
 
 def sdf_bce_step(octree: FeatureOctree, decoder: Decoder, coord, sdf_label, sigma, weight=None, weighted=False,
-                 bce_reduction="mean", n_norm=None, single_pass=True, tf32x1=False, return_pred=False):
+                 bce_reduction="mean", n_norm=None, single_pass=True, tf32x1=False, return_pred=False,
+                 morton_ordered=False):
     """loss (= sdf_bce_loss(decoder.sdf(octree.query_feature(coord)), sdf_label, sigma, |weight|, weighted,
     reduction)) with autograd to `octree.hier_features` and the decoder parameters.
 
-    n_norm: denominator of the "mean" (defaults to len(coord); pass the GLOBAL batch when sharding points)."""
+    n_norm: denominator of the "mean" (defaults to len(coord); pass the GLOBAL batch when sharding points).
+    morton_ordered: the batch is in Morton order (see SdfTrainer.forward_backward); a performance hint."""
     if coord.requires_grad:
         raise NotImplementedError("gradients w.r.t. coordinates are not part of the fused sm_100a path")
     coord, sdf_label = _prep(coord, "coord"), _prep(sdf_label, "sdf_label")
@@ -128,7 +133,8 @@ def sdf_bce_step(octree: FeatureOctree, decoder: Decoder, coord, sdf_label, sigm
     # autograd.Function cannot take None among *tensor* args transparently for needs_input_grad bookkeeping,
     # so bias-less decoders pass None placeholders which are skipped in backward.
     loss, pred = _SdfBce.apply(octree, decoder, coord, sdf_label, weight, float(sigma), bool(weighted),
-                               bce_reduction, n_norm, single_pass, tf32x1, *params)
+                               bce_reduction, n_norm, single_pass,
+                               (_abi.FLAG_TF32X1 if tf32x1 else 0) | (_abi.FLAG_MORTON_ORDERED if morton_ordered else 0), *params)
     return (loss, pred) if return_pred else loss
 
 

@@ -96,24 +96,48 @@ def sample_rays(points_scaled: torch.Tensor, origin_scaled: torch.Tensor, config
 
 
 class SamplePool:
-    """coord / sdf_label / weight pools + `get_batch()` (dataset/lidar_dataset.py:431-448)."""
+    """coord / sdf_label / weight pools + `get_batch()` (dataset/lidar_dataset.py:431-448).
+
+    `sort_morton()` puts the pool in Morton order of the sample coordinates (once, when the map is built).  From then on
+    `get_batch()` draws the SAME random index multiset as the reference (`torch.randint`, with replacement) and hands the
+    samples out in ascending index order, i.e. in Morton order: neighbouring points of a batch then touch the same octree
+    nodes, which is what the gather (L1 hits) and the voxel-grouped scatter of the training kernel feed on
+    (`SdfTrainer.forward_backward(..., morton_ordered=pool.ordered)`).  The loss of a batch does not depend on its order."""
 
     def __init__(self, device):
         self.device = device
         self.coord_pool = torch.empty(0, 3, device=device)
         self.sdf_label_pool = torch.empty(0, device=device)
         self.weight_pool = torch.empty(0, device=device)
+        self.ordered = False
 
     def append(self, coord, label, weight):
         self.coord_pool = torch.cat((self.coord_pool, coord.to(self.device)))
         self.sdf_label_pool = torch.cat((self.sdf_label_pool, label.to(self.device)))
         self.weight_pool = torch.cat((self.weight_pool, weight.to(self.device)))
+        self.ordered = False
 
     def __len__(self):
         return self.sdf_label_pool.shape[0]
 
-    def get_batch(self, bs: int, generator: torch.Generator | None = None):
+    def sort_morton(self, level: int = 16):
+        """Reorder the pool along the Z-order curve of a 2^level grid over [-1, 1]^3 (16: kaolin's int16 coordinates)."""
+        from .feature_octree import points_to_morton, quantize_points
+        if len(self):
+            order = torch.argsort(points_to_morton(quantize_points(self.coord_pool, level)))
+            self.coord_pool = self.coord_pool[order].contiguous()
+            self.sdf_label_pool = self.sdf_label_pool[order].contiguous()
+            self.weight_pool = self.weight_pool[order].contiguous()
+        self.ordered = True
+        return self
+
+    def get_batch(self, bs: int, generator: torch.Generator | None = None, ordered: bool | None = None):
+        """ordered: None = Morton order iff the pool is sorted; False = the reference's order (as drawn)."""
         index = torch.randint(0, len(self), (bs,), device=self.device, generator=generator)
+        if self.ordered and ordered is not False:
+            index = torch.sort(index).values
+        elif ordered:
+            raise ValueError("ordered batches need a pool in Morton order: call sort_morton() first")
         return self.coord_pool[index, :], self.sdf_label_pool[index], self.weight_pool[index]
 
 

@@ -111,11 +111,14 @@ class SdfTrainer:
     # ---- the hot path --------------------------------------------------------------------------------------
 
     def forward_backward(self, coord, sdf_label, weight=None, n_norm=None, pred_out=None, accumulate_loss=False,
-                         weighted=None, mid_event=None):
+                         weighted=None, mid_event=None, morton_ordered=False):
         """One fused launch: loss value (device scalar, accumulated into self.loss which is zeroed here) and
         gradients accumulated into the flat buffer.  Caller zeroes grads (zero_grad / fused in optimizer_step).
         weighted: None = config.loss_weight_on (the loop, shine_batch.py:174); False = unweighted BCE whatever the
-        config says (what cal_feature_importance uses, utils/incre_learning.py:33)."""
+        config says (what cal_feature_importance uses, utils/incre_learning.py:33).
+        morton_ordered: the batch comes in Morton order of its coordinates (`DataPool.get_batch(..., ordered=True)`):
+        the kernel then sums the table gradients per run of equal node before the atomics (same result up to fp32
+        summation order; a hint only, any batch is handled correctly)."""
         self._sync()
         cfg = self.config
         n = coord.shape[0]
@@ -124,7 +127,7 @@ class SdfTrainer:
             raise ValueError("loss_weight_on needs the per-sample weight tensor")
         flags = (_abi.FLAG_REDUCTION_SUM if cfg.loss_reduction == "sum" else 0) | \
                 (_abi.FLAG_WEIGHTED if weighted else 0) | (_abi.FLAG_TF32X1 if self.tf32x1 else 0) | \
-                (_abi.FLAG_TCGEN05 if self.tcgen05 else 0)
+                (_abi.FLAG_TCGEN05 if self.tcgen05 else 0) | (_abi.FLAG_MORTON_ORDERED if morton_ordered else 0)
         scale = 1.0 if cfg.loss_reduction == "sum" else 1.0 / float(n_norm if n_norm else n)
         od = self.octree._descriptor(None, self.table_grads, n_points=n if self.use_replicas else 0)
         dd = self.decoder.c_descriptor(self.dec_grads if self._dec_trainable else None)

@@ -80,6 +80,16 @@ def make_case(n_points=3000, n_batch=2048, feat_levels=2, seed=0, n_frames=1, po
     }
 
 
+def sort_case_morton(case, level=12):
+    """The same batch in Morton order of its coordinates (what the sorted sample pool hands out)."""
+    from shine_mapping_b200.feature_octree import points_to_morton, quantize_points
+    order = torch.argsort(points_to_morton(quantize_points(torch.from_numpy(case["coord"]), level)), stable=True).numpy()
+    out = dict(case)
+    for k in ("coord", "label", "weight"):
+        out[k] = np.ascontiguousarray(case[k][order])
+    return out
+
+
 def drop_relu_kink_points(case, eps=2e-6):
     """Remove the (very few) batch points that have a decoder pre-activation within `eps` of zero.  At a ReLU kink two
     fp32-grade implementations that sum in a different order can land on different sides; the gradient of that one point
@@ -151,9 +161,10 @@ def build_cuda_models(case, device="cuda:0", freeze_decoder=False):
     return cfg, octree, dec
 
 
-def run_cuda_step(case, device="cuda:0", single_pass=True, tf32x1=False, unfused=False):
+def run_cuda_step(case, device="cuda:0", single_pass=True, tf32x1=False, unfused=False, morton_ordered=False,
+                  freeze_decoder=False):
     from shine_mapping_b200 import sdf_bce_loss, sdf_bce_step
-    cfg, octree, dec = build_cuda_models(case, device)
+    cfg, octree, dec = build_cuda_models(case, device, freeze_decoder=freeze_decoder)
     c = case["cfg"]
     coord = torch.from_numpy(case["coord"]).to(device); label = torch.from_numpy(case["label"]).to(device)
     weight = torch.from_numpy(case["weight"]).to(device)
@@ -164,14 +175,14 @@ def run_cuda_step(case, device="cuda:0", single_pass=True, tf32x1=False, unfused
         loss = sdf_bce_loss(pred, label, c["sigma"], torch.abs(weight), c["weighted"], c["reduction"])
     else:
         loss, pred = sdf_bce_step(octree, dec, coord, label, c["sigma"], weight, c["weighted"], c["reduction"],
-                                  single_pass=single_pass, tf32x1=tf32x1, return_pred=True)
+                                  single_pass=single_pass, tf32x1=tf32x1, return_pred=True, morton_ordered=morton_ordered)
     loss.backward()
     torch.cuda.synchronize()
     return {
         "indices": indices, "feature": feature.detach().cpu().numpy(), "pred": pred.detach().cpu().numpy(),
         "loss": float(loss.detach()),
         "table_grads": [p.grad.cpu().numpy() for p in octree.hier_features],
-        "dec_grads": {k: dict(dec.named_parameters())[k].grad.cpu().numpy() for k in DEC_KEYS},
+        "dec_grads": {} if freeze_decoder else {k: dict(dec.named_parameters())[k].grad.cpu().numpy() for k in DEC_KEYS},
     }
 
 

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from tests.parity_utils import (DEC_KEYS, GOLDEN_NAMES, build_cuda_models, compare_step, load_golden, make_case,
-                                run_cuda_step, run_oracle_step)
+                                run_cuda_step, run_oracle_step, sort_case_morton)
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -41,6 +41,38 @@ def test_fused_step_matches_oracle(levels, poly, weighted, reduction, frames):
     case = make_case(n_points=2500, n_batch=3000, feat_levels=levels, seed=10 + levels, n_frames=frames,
                      poly=poly, weighted=weighted, reduction=reduction)
     print(compare_step(run_cuda_step(case, DEV), run_oracle_step(case)))
+
+
+@pytest.mark.parametrize("levels,poly,weighted,reduction,ordered", [
+    (1, True, False, "mean", True), (2, False, True, "sum", True), (3, True, False, "mean", True),
+    (4, True, True, "mean", True), (4, True, False, "mean", False), (3, False, False, "sum", False),
+    (6, True, False, "mean", True),      # > 4 levels: the flag falls back to the general kernel
+])
+def test_grouped_scatter_matches_oracle(levels, poly, weighted, reduction, ordered):
+    """SHINE_FLAG_MORTON_ORDERED: per-run tensor-core reduction of the table gradients.  Batches in Morton order (runs of
+    equal node, several per tile) and in random order (the hint is wrong: every level of every tile takes the per-point
+    path) must both match the oracle; a frozen decoder exercises the kernel flavour without the staging area."""
+    case = make_case(n_points=2500, n_batch=6000, feat_levels=levels, seed=40 + levels, n_frames=1,
+                     poly=poly, weighted=weighted, reduction=reduction)
+    if ordered:
+        case = sort_case_morton(case)
+    want = run_oracle_step(case)
+    print(compare_step(run_cuda_step(case, DEV, morton_ordered=True), want))
+    want_f = dict(want); want_f["dec_grads"] = {}
+    print(compare_step(run_cuda_step(case, DEV, morton_ordered=True, freeze_decoder=True), want_f))
+
+
+def test_grouped_scatter_dense_runs():
+    """Many samples per voxel (16-point tiles inside ONE node at every level, runs crossing tile borders)."""
+    case = make_case(n_points=2500, n_batch=64, feat_levels=3, seed=77)
+    rng = np.random.default_rng(5)
+    base = case["coord"][rng.integers(0, 64, size=24)]
+    coord = (base[:, None, :] + rng.uniform(-2e-4, 2e-4, size=(24, 200, 3))).reshape(-1, 3).astype(np.float32)
+    case["coord"] = coord
+    case["label"] = rng.uniform(-0.05, 0.05, size=coord.shape[0]).astype(np.float32)
+    case["weight"] = np.ones(coord.shape[0], dtype=np.float32)
+    case = sort_case_morton(case)
+    print(compare_step(run_cuda_step(case, DEV, morton_ordered=True), run_oracle_step(case)))
 
 
 @pytest.mark.parametrize("n_batch", [0, 1, 15, 16, 17, 255])

@@ -46,12 +46,14 @@ def timeit(fn, name, bytes_per_pt=None):
 tr3 = SdfTrainer(cfg, octree, decoder)
 tr1 = SdfTrainer(cfg, octree, decoder, tf32x1=True)
 timeit(lambda: tr3.forward_backward(coord, label), "step 3xTF32 dec_grad")
+timeit(lambda: tr3.forward_backward(coord, label, morton_ordered=True), "step 3xTF32 dec_grad grouped")
 trtc = SdfTrainer(cfg, octree, decoder, tcgen05=True)
 timeit(lambda: trtc.forward_backward(coord, label), "step tcgen05 3xTF32 dec_grad")
 if not args.quick: timeit(lambda: tr1.forward_backward(coord, label), "step 1xTF32 dec_grad")
 for p in decoder.parameters(): p.requires_grad = False
 trf3 = SdfTrainer(cfg, octree, decoder); trf1 = SdfTrainer(cfg, octree, decoder, tf32x1=True)
 timeit(lambda: trf3.forward_backward(coord, label), "step 3xTF32 frozen decoder")
+timeit(lambda: trf3.forward_backward(coord, label, morton_ordered=True), "step 3xTF32 frozen grouped")
 timeit(lambda: sdf_infer(octree, decoder, coord), "infer 3xTF32")
 if args.quick: sys.exit(0)
 timeit(lambda: trf1.forward_backward(coord, label), "step 1xTF32 frozen decoder")
