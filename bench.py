@@ -111,9 +111,16 @@ def build_partitioned_workload(device, rank, world, n_azimuth, n_frames=None, ex
     return cfg, octree, decoder, pool, plan, comm, p2p, info
 
 
-def shared_config(cfg, n_azimuth, pool_len, n, world, rows):
+BATCH_ORDER_NOTE = {
+    "morton": "randint-drawn samples (with replacement, the reference's sampler) handed out in Morton order of their "
+              "coordinates (SamplePool.sort_morton + sorted indices); the loss of a batch does not depend on its order",
+    "random": "randint-drawn samples in the order drawn (the reference's order)"}
+
+
+def shared_config(cfg, n_azimuth, pool_len, n, world, rows, batch_order="morton"):
     """The `config` object of the JSON line — identical for our arm and the reference arm (same workload, same N)."""
     return {"workload": cfg.name, "n_azimuth": n_azimuth, "pool_samples": pool_len, "points_per_step_per_gpu": n,
+            "batch_order": batch_order, "batch_order_note": BATCH_ORDER_NOTE[batch_order],
             "global_points_per_step": n * world, "tree_level_feat": L, "feature_dim": F, "table_rows": rows,
             "decoder": "geo_decoder_8dim arch 8-32-32-1, trainable", "loss": "sdf_bce mean",
             "step": "grad zero + fwd + loss + bwd (table scatter-add + decoder grads); no optimizer"}
@@ -240,6 +247,8 @@ def run_reference(args):
     n = len(pool) if args.points <= 0 else args.points
     sample = n if args.ref_sample <= 0 else min(n, args.ref_sample)
     gen = torch.Generator().manual_seed(7)
+    if args.batch_order == "morton":
+        pool.sort_morton()
     batches = [pool.get_batch(sample, gen) for _ in range(2)]
     pick_threads(orc, o, dec, tuple(t[:20000] for t in batches[0]), cfg.sigma_sigmoid)
     ts = time_oracle(orc, o, dec, batches, cfg.sigma_sigmoid, args.steps, args.warmup)
@@ -250,7 +259,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": shared_config(cfg, args.n_azimuth, len(pool), n, max(args.gpus, 1),
-                                [int(p.shape[0]) for p in octree.hier_features]),
+                                [int(p.shape[0]) for p in octree.hier_features], args.batch_order),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{sample} randint-drawn samples of the {len(pool)}-sample C2 scan per step "
                                    f"(= the points_per_step_per_gpu of our arm)" if sample == n else
@@ -276,6 +285,22 @@ def kernel_counters():
     return base
 
 
+def e2e_record(n, n_global, pipe_sec, sync_sec, n_host, loss_last):
+    """Both public host-step calls are timed on the same pinned host batches; the better one is the e2e figure (which
+    one wins depends on the box: the copy engines' rate from host memory decides), the other is kept beside it."""
+    modes = {"pipelined": {"value": n_global / pipe_sec, "ms_per_step": pipe_sec * 1e3,
+                           "mode": "submit_host_step()/result(): step k+1's host->device copy under step k's kernels, depth 2"},
+             "sync": {"value": n_global / sync_sec, "ms_per_step": sync_sec * 1e3,
+                      "mode": "step_from_host(): chunked copy, step and loss read-back strictly inside one call"}}
+    best = "pipelined" if pipe_sec <= sync_sec else "sync"
+    other = "sync" if best == "pipelined" else "pipelined"
+    rec = {"value": modes[best]["value"], "unit": UNIT, "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": 4,
+           "ms_per_step": modes[best]["ms_per_step"], "mode": modes[best]["mode"], "host_batches": n_host,
+           "h2d_gbps": n * 16 / (modes[best]["ms_per_step"] * 1e-3) / 1e9, "loss_last": loss_last}
+    rec[other] = modes[other]
+    return rec
+
+
 def time_steps(trainer, batches, steps, flush_buf, n_norm, dev, all_reduce=True):
     """K steps with the L2 flushed before each; -> per-step (zero+kernel+reduce+allreduce), fused kernel alone, replica
     reduce alone, in ms (means).  CUDA events on the launching stream."""
@@ -299,8 +324,7 @@ def time_steps(trainer, batches, steps, flush_buf, n_norm, dev, all_reduce=True)
 
 
 def parity_block(orc, o, dec, trainer, octree, decoder, batch, sample, sigma):
-    """CUDA step vs the oracle on the first `sample` points of a bench batch (the oracle results of the cpu_baseline
-    leg are kept instead of being thrown away)."""
+    """CUDA step (the trainer of the timed steps: same kernel flavour) vs the oracle on `sample` points of a bench batch."""
     import numpy as np
     c, l = batch[0][:sample].contiguous(), batch[1][:sample].contiguous()
     res = orc.train_step(o, dec, c.cpu(), l.cpu(), None, sigma, False, "mean")
@@ -392,6 +416,7 @@ def hbm_leg(args, dev, peak):
     del flush_buf
     return {
         "bound": "hbm", "kernel": "sdf_fused_kernel<3,train,dec_grad,4>", "workload": cfg.name,
+        "batch_order": "random (the order drawn: the access pattern that makes this leg HBM-bound)",
         "frames": args.hbm_frames, "table_rows": rows, "table_mb": table_mb, "grad_mb": table_mb,
         "points_per_step": n, "build_s": round(build_s, 1),
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -501,16 +526,20 @@ def run_ours(args):
     torch.cuda.set_device(dev)
     numa = sdist.pin_to_gpu_numa_node(local) if world > 1 else {"numa_node": sdist.gpu_numa_node(local), "cpus": None}
     part_info = None
+    ordered = args.batch_order == "morton"
     if world > 1:
         cfg, octree, decoder, pool, plan, comm, p2p, part_info = build_partitioned_workload(
             str(dev), rank, world, args.n_azimuth, exchange=args.exchange)
         # weak scaling: every GPU steps as many points as the single GPU does (one scan's worth), drawn from ITS range
         n = (args.points if args.points > 0 else C2_POINTS_PER_STEP) if args.global_points <= 0 else args.global_points // world
-        trainer = SdfTrainer(cfg, octree, decoder, shard_mode="spatial", boundary=plan, comm=comm, p2p=p2p)
+        trainer = SdfTrainer(cfg, octree, decoder, shard_mode="spatial", boundary=plan, comm=comm, p2p=p2p,
+                             morton_ordered=ordered)
     else:
         cfg, octree, decoder, pool = build_workload(str(dev), rank, world, args.n_azimuth)
         n = len(pool) if args.points <= 0 else args.points
-        trainer = SdfTrainer(cfg, octree, decoder, shard_mode="spatial")
+        trainer = SdfTrainer(cfg, octree, decoder, shard_mode="spatial", morton_ordered=ordered)
+    if ordered:
+        pool.sort_morton()      # once, with the map; batches are then handed out in Morton order
     n_global = n * world
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     batches = [pool.get_batch(n, gen) for _ in range(4)]
@@ -544,6 +573,17 @@ def run_ours(args):
     kern_ms_max = sdist.max_over_ranks(kern_ms, dev)
     red_ms_max = sdist.max_over_ranks(red_ms, dev)
     exch_ms = getattr(time_steps, "last_exchange_ms", 0.0)
+    other_order = None
+    if world == 1 and ordered:      # the same step on batches in the order drawn (general kernel), for the record
+        tr_r = SdfTrainer(cfg, octree, decoder, shard_mode="spatial", morton_ordered=False)
+        br = [pool.get_batch(n, gen, ordered=False) for _ in range(2)]
+        for i in range(3):
+            tr_r.zero_grad(); tr_r.forward_backward(br[i % 2][0], br[i % 2][1], None, n_norm=n_global)
+        r_step, r_kern, _ = time_steps(tr_r, br, args.steps, flush_buf, n_global, dev)
+        other_order = {"batch_order": "random", "value": n_global / (r_step * 1e-3), "ms_per_step": r_step,
+                       "kernel_ms": r_kern, "kernel": "sdf_fused_kernel<3,train,dec_grad,4> (per-point reds)",
+                       "note": BATCH_ORDER_NOTE["random"]}
+        del tr_r, br
     exch_ms_max = sdist.max_over_ranks(exch_ms, dev)
     exch_ms_min = -sdist.max_over_ranks(-exch_ms, dev)
     kern_ms_min = -sdist.max_over_ranks(-kern_ms, dev)
@@ -581,7 +621,7 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     e2e_sec = sdist.max_over_ranks((time.perf_counter() - t0) / args.steps, dev)
     e2e_value = n_global / e2e_sec
-    for i in range(4):            # synchronous variant: every pinned host batch once -> its CUDA graph is captured untimed
+    for i in range(n_host):       # synchronous variant: every pinned host batch once -> its CUDA graph is captured untimed
         trainer.step_from_host(*host[i])
     sync_ts = []
     sdist.barrier(dev); torch.cuda.synchronize(dev)
@@ -589,7 +629,7 @@ def run_ours(args):
         flush_buf.fill_(k & 0xFF)
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        trainer.step_from_host(*host[k % 4])          # ends with loss.item(): device -> host read
+        trainer.step_from_host(*host[k % n_host])     # ends with loss.item(): device -> host read
         if world > 1:
             trainer.all_reduce_grads(); torch.cuda.synchronize(dev)
         sync_ts.append(time.perf_counter() - t0)
@@ -611,8 +651,9 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": shared_config(cfg, args.n_azimuth, len(pool), n, world, rows),
+        "config": shared_config(cfg, args.n_azimuth, len(pool), n, world, rows, args.batch_order),
         "impl_notes": {"decoder_math": "3xTF32 mma.sync (fp32-grade)",
+                       "other_batch_order": other_order,
                        "parallelism": "single GPU" if world == 1 else
                        f"one map, Morton-prefix ranges x{world}; ONE exchange per step over [decoder grads | "
                        "gradients of corner rows shared between ranges] (see partition.exchange)",
@@ -624,7 +665,8 @@ def run_ours(args):
                        "timed_step": "grad memset + fused fwd+loss+bwd kernel + replica fold (+ all-reduce when N>1)"},
         # the C2 map (2.75 MB of features) lives in L2: the kernel's physical bound there is the L1TEX LSU data pipe
         # (1 wavefront / clk / SM), not HBM.  wavefronts/point come from the committed ncu capture, time is live.
-        "roofline": {"bound": "l1tex_lsu", "kernel": "sdf_fused_kernel<3,train,dec_grad,4>",
+        "roofline": {"bound": "l1tex_lsu",
+                     "kernel": "sdf_fused_kernel<3,train,dec_grad,4" + (",grouped>" if ordered else ">"),
                      "achieved": wf_rate, "peak": wf_peak, "unit": "Gwavefront/s", "frac": wf_rate / wf_peak,
                      "traffic": cnt["c2"]["dram_bytes_per_point"] * n, "kernel_ms": kern_ms_max,
                      "replica_reduce_ms": red_ms_max,
@@ -634,11 +676,7 @@ def run_ours(args):
                      "algorithmic_over_hbm_peak": alg / peak,
                      "note": "algorithmic bytes / time exceeds the HBM peak because >98 % of them are served by L2 "
                              "(measured DRAM traffic in `traffic`); the HBM roofline proper is `roofline_hbm`"},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * 16, "d2h_bytes_per_step": 4,
-                "ms_per_step": e2e_sec * 1e3, "mode": "pipelined submit_host_step()/result(), depth 2",
-                "host_batches": n_host, "loss_last": losses[-1],
-                "sync": {"value": n_global / e2e_sync_sec, "ms_per_step": e2e_sync_sec * 1e3,
-                         "mode": "step_from_host(): copy, step and loss read-back strictly inside one call"}},
+        "e2e": e2e_record(n, n_global, e2e_sec, e2e_sync_sec, n_host, losses[-1]),
         "gpu_launches": launches,
         "clocks": clocks,
         "host": {"numa": numa, "cpu_count": os.cpu_count(), "affinity": len(os.sched_getaffinity(0))},
@@ -649,17 +687,21 @@ def run_ours(args):
         line["roofline_hbm"] = hbm_leg(args, dev, peak)
         line["roofline_hbm"]["peak_source"] = peak_src
     if world == 1 and not args.no_cpu_baseline:
+        was_ordered, pool.ordered = pool.ordered, False      # the reference's batch sizes in the reference's order
         line["small_batch"] = small_batch_records(cfg, octree, decoder, pool, dev)
+        pool.ordered = was_ordered
         torch.set_num_threads(os.cpu_count() or 1)
         orc, o, dec = oracle_from_octree(octree, decoder)
         sample = min(n, args.ref_sample if args.ref_sample > 0 else 100000)
-        cb = [tuple(t[:sample].cpu() for t in b) for b in batches[:2]]
+        stride = max(1, n // sample)      # every stride-th point: a subsequence of a Morton-ordered batch is Morton-ordered
+        sub = [tuple(t[::stride][:sample].contiguous() for t in b) for b in batches[:2]]
+        cb = [tuple(t.cpu() for t in b) for b in sub]
         pick_threads(orc, o, dec, tuple(t[:20000] for t in cb[0]), cfg.sigma_sigmoid)
         ts = time_oracle(orc, o, dec, cb, cfg.sigma_sigmoid, 3, 1)
         line["cpu_baseline"] = {"value": sample / statistics.mean(ts), "unit": UNIT, "cores": torch.get_num_threads(),
-                                "kind": "port", "sample": f"first {sample} points of the step's batch, 1 warm-up + 3 "
+                                "kind": "port", "sample": f"every {stride}-th point ({sample}) of the step's batch, 1 warm-up + 3 "
                                                            "timed oracle steps (Python-dict lookup + torch CPU autograd)"}
-        line["parity"] = parity_block(orc, o, dec, trainer, octree, decoder, batches[0], sample, cfg.sigma_sigmoid)
+        line["parity"] = parity_block(orc, o, dec, trainer, octree, decoder, sub[0], sample, cfg.sigma_sigmoid)
         line["configs"] = other_config_records(dev)
     print(json.dumps(line), flush=True)
 
@@ -681,6 +723,8 @@ def main():
     ap.add_argument("--hbm-points", type=int, default=1 << 20, help="points per step of the HBM-bound leg")
     ap.add_argument("--exchange", default=os.environ.get("SHINE_EXCHANGE", "auto"), choices=["auto", "nccl", "p2p"],
                     help="N>1: the step's exchange — NCCL all-reduce through the C ABI, or the one-kernel NVLink peer-memory path")
+    ap.add_argument("--batch-order", default="morton", choices=["morton", "random"],
+                    help="order the sampler hands a batch out in (same random index multiset either way)")
     ap.add_argument("--no-hbm-leg", action="store_true")
     ap.add_argument("--hbm-only", action="store_true", help="run only the HBM-bound leg and print its object (ncu target)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

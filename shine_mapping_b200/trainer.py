@@ -28,7 +28,8 @@ def _align4(n: int) -> int:
 
 class SdfTrainer:
     def __init__(self, config: SHINEConfig, octree: FeatureOctree, decoder: Decoder, process_group=None,
-                 tf32x1: bool = False, shard_mode: str = "replicated", boundary=None, comm=None, tcgen05=None, p2p=None):
+                 tf32x1: bool = False, shard_mode: str = "replicated", boundary=None, comm=None, tcgen05=None, p2p=None,
+                 morton_ordered: bool = False):
         """shard_mode (multi-GPU, see dist.py / partition.py): "replicated" = every rank holds the whole table and a
         slice of the point batch -> all-reduce the whole flat gradient; "spatial" = every rank owns a Morton-prefix
         range of ONE map and the samples inside it (BASELINE config 5) -> ONE all-reduce over
@@ -43,6 +44,7 @@ class SdfTrainer:
         # gradient replicas for small hot levels (see FeatureOctree._replicas_for); on by default for big batches
         self.use_replicas = os.environ.get("SHINE_FUSED_REPLICAS", "1") != "0"
         self.group = process_group
+        self.morton_ordered = bool(morton_ordered)   # default for every step: batches come from a Morton-sorted SamplePool
         self.tf32x1 = tf32x1
         # decoder of the fused step on tcgen05.mma / TMEM (csrc/shine_train_tc.cu); None = the library default
         self.tcgen05 = (os.environ.get("SHINE_TRAIN_TCGEN05", "0") == "1") if tcgen05 is None else bool(tcgen05)
@@ -111,14 +113,14 @@ class SdfTrainer:
     # ---- the hot path --------------------------------------------------------------------------------------
 
     def forward_backward(self, coord, sdf_label, weight=None, n_norm=None, pred_out=None, accumulate_loss=False,
-                         weighted=None, mid_event=None, morton_ordered=False):
+                         weighted=None, mid_event=None, morton_ordered=None):
         """One fused launch: loss value (device scalar, accumulated into self.loss which is zeroed here) and
         gradients accumulated into the flat buffer.  Caller zeroes grads (zero_grad / fused in optimizer_step).
         weighted: None = config.loss_weight_on (the loop, shine_batch.py:174); False = unweighted BCE whatever the
         config says (what cal_feature_importance uses, utils/incre_learning.py:33).
         morton_ordered: the batch comes in Morton order of its coordinates (`DataPool.get_batch(..., ordered=True)`):
         the kernel then sums the table gradients per run of equal node before the atomics (same result up to fp32
-        summation order; a hint only, any batch is handled correctly)."""
+        summation order; a hint only, any batch is handled correctly).  None = the trainer's `morton_ordered` default."""
         self._sync()
         cfg = self.config
         n = coord.shape[0]
@@ -127,7 +129,8 @@ class SdfTrainer:
             raise ValueError("loss_weight_on needs the per-sample weight tensor")
         flags = (_abi.FLAG_REDUCTION_SUM if cfg.loss_reduction == "sum" else 0) | \
                 (_abi.FLAG_WEIGHTED if weighted else 0) | (_abi.FLAG_TF32X1 if self.tf32x1 else 0) | \
-                (_abi.FLAG_TCGEN05 if self.tcgen05 else 0) | (_abi.FLAG_MORTON_ORDERED if morton_ordered else 0)
+                (_abi.FLAG_TCGEN05 if self.tcgen05 else 0) | \
+                (_abi.FLAG_MORTON_ORDERED if (self.morton_ordered if morton_ordered is None else morton_ordered) else 0)
         scale = 1.0 if cfg.loss_reduction == "sum" else 1.0 / float(n_norm if n_norm else n)
         od = self.octree._descriptor(None, self.table_grads, n_points=n if self.use_replicas else 0)
         dd = self.decoder.c_descriptor(self.dec_grads if self._dec_trainable else None)

@@ -1,14 +1,17 @@
 #!/usr/bin/env python
 """profiles/r02_kernel_counters.json from the two `ncu --set full` captures of bench.py (C2 step, HBM-bound leg).
 
-usage: python tools/ncu_counters.py gpurun_out/r02_step_c2.ncu-rep gpurun_out/r02_step_hbm.ncu-rep
+usage: python tools/ncu_counters.py c2=gpurun_out/r02_step_c2_grouped.ncu-rep c2_random=gpurun_out/r02_step_c2.ncu-rep \
+           hbm=gpurun_out/r02_step_hbm.ncu-rep
+(c2 = the kernel of the bench's timed steps: Morton-ordered batches, voxel-grouped scatter; c2_random = the general kernel
+on batches in the order drawn; hbm = the general kernel on the 328 MB map).  Entries not named keep their old values.
 Reads the raw page (`ncu -i REP --page raw --csv --print-units base`), keeps the per-launch counters bench.py turns into
 rooflines and writes the details pages next to the json (profiles/r02_step_{c2,hbm}_details.csv).
 """
 import csv, io, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-POINTS = {"c2": 776616, "hbm": 1048576}
+POINTS = {"c2": 776616, "c2_random": 776616, "hbm": 1048576}
 SMS = 148
 
 
@@ -27,8 +30,9 @@ def num(d, key):
 
 
 def main():
-    reps = {"c2": sys.argv[1], "hbm": sys.argv[2]}
-    res = {}
+    reps = dict(a.split("=", 1) for a in sys.argv[1:])
+    out_path = os.path.join(ROOT, "profiles", "r02_kernel_counters.json")
+    res = json.load(open(out_path)) if os.path.exists(out_path) else {}
     for name, rep in reps.items():
         d = raw(rep)
         pts = POINTS[name]
@@ -50,7 +54,7 @@ def main():
         }
         det = subprocess.run(["ncu", "-i", rep, "--page", "details", "--csv"], capture_output=True, text=True, check=True).stdout
         open(os.path.join(ROOT, "profiles", f"r02_step_{name}_details.csv"), "w").write(det)
-    json.dump(res, open(os.path.join(ROOT, "profiles", "r02_kernel_counters.json"), "w"), indent=1)
+    json.dump(res, open(out_path, "w"), indent=1)
     print(json.dumps(res, indent=1))
 
 
