@@ -303,6 +303,8 @@ const char* shine_comm_last_error(void);
 typedef struct shine_boundary_inverse {
     const int32_t* row_of_slot[SHINE_MAX_LEVELS];   /* [slots of the level] local row holding that shared corner, -1 if none */
     int32_t slots[SHINE_MAX_LEVELS];                /* length of the level's globally agreed boundary list           */
+    const int32_t* holders[SHINE_MAX_LEVELS];       /* [slots] bit r set: rank r holds a row of that corner (its buffer is
+                                                       read for the sum); NULL: every rank's buffer is read            */
 } shine_boundary_inverse;
 typedef struct shine_p2p shine_p2p;
 int shine_p2p_create(int32_t nranks, int32_t rank, int32_t device, int64_t max_floats, void* out_handle64, shine_p2p** out);

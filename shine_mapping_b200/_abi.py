@@ -87,7 +87,8 @@ class ShineBuild(C.Structure):
 
 
 class ShineBoundaryInverse(C.Structure):
-    _fields_ = [("row_of_slot", C.c_void_p * MAX_LEVELS), ("slots", C.c_int32 * MAX_LEVELS)]
+    _fields_ = [("row_of_slot", C.c_void_p * MAX_LEVELS), ("slots", C.c_int32 * MAX_LEVELS),
+                ("holders", C.c_void_p * MAX_LEVELS)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/shine_b200.h

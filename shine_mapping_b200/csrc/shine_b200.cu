@@ -348,9 +348,8 @@ struct SmemPlan {
     static constexpr int B2 = B1 + kH;
     static constexpr int W3 = B2 + kH;
     static constexpr int B3 = W3 + kH;                 // [1] (+3 pad)
-    static constexpr int RED = B3 + 4;                 // block accumulator for decoder grads [1377 -> 1380]
-    static constexpr int kDecGradFloats = kH * kF + kH + kH * kH + kH + kH + 1;   // 1377
-    static constexpr int PRE = RED + 1380;             // per-warp input prefetch: [16][3] coord | [16] label | [16] weight
+    static constexpr int kDecGradFloats = kH * kF + kH + kH * kH + kH + kH + 1;   // 1377 (a warp's partial goes to its staging area)
+    static constexpr int PRE = B3 + 4;                 // per-warp input prefetch: [16][3] coord | [16] label | [16] weight
     static constexpr int kPrePerWarp = 5 * kTile;
     static constexpr int STAGE = PRE + 8 * kPrePerWarp;   // per-warp staging: 3 x [16][kWS] + [16][8]
     static constexpr int kStagePerWarp = 3 * kTile * kWS + kTile * kF;   // dh2 | h1 | dh1 | feat tiles
@@ -360,13 +359,13 @@ struct SmemPlan {
 };
 
 // ---- voxel-grouped scatter (GROUPED kernels: batches in Morton order) ---------------------------------------------
-// In a Morton-ordered batch the 16 points of a tile fall into a few runs of equal node per level.  The per-run gradient
-// of the node's 8 corner rows is a small contraction over the run's points,
+// In a Morton-ordered batch the 16 points of a tile fall into a few groups of equal node per level.  The per-group gradient
+// of the node's 8 corner rows is a small contraction over the group's points,
 //     G[corner][channel] = sum_p w_corner(p) * dL/dfeature(p)[channel]          (8 x npts) x (npts x 8),
-// so it runs on the tensor cores (m16n8k8, 3xTF32, rows 0-7 = corners of one run, rows 8-15 = corners of the next) and
-// each run issues ONE 8-byte red per lane (8 rows x 32 B per instruction) instead of one 16-byte red per point and corner:
+// so it runs on the tensor cores (m16n8k8, 3xTF32, rows 0-7 = corners of one group, rows 8-15 = corners of the next) and
+// each group issues ONE 8-byte red per lane (8 rows x 32 B per instruction) instead of one 16-byte red per point and corner:
 // the same-address atomics that serialise in L2 when neighbouring points share a voxel disappear.  Correct for any order
-// (a level with more than kMaxGroupedRuns runs takes the per-point path).
+// (a level with more than kMaxGroupedRuns groups in a tile takes the per-point path).
 constexpr int kMaxGroupedRuns = 6;
 
 __device__ __forceinline__ void red_add_f2(float* p, float a, float b) {
@@ -393,17 +392,20 @@ __device__ __forceinline__ void grouped_scatter(const StepParams& P, int L, int 
     const float sy = (g & 2) ? 1.f : -1.f, oy = (g & 2) ? 0.f : 1.f;
     const float sz = (g & 1) ? 1.f : -1.f, oz = (g & 1) ? 0.f : 1.f;
     const int id_off = 8 * (g & 1) + 4 + (g >> 1);            // word of corner g's row index inside a 16-word HashSlot
-    const int own = group_slot(lane & 15), prev = group_slot((lane + 15) & 15);
+    const int own = group_slot(lane & 15);
 #pragma unroll
     for (int i = 0; i < LMAX; ++i) {
         if (i >= L) break;
         const float* lt = pt + i * SmemPlan::kGroupPerLevel;
-        // run structure of the level: point p starts a run when its node differs from point p-1's (lanes 0..15 <-> points)
+        // groups of the level: the points of the tile that fall into the same node (lanes 0..15 <-> points; the upper half
+        // of the warp mirrors them).  The lowest lane of a group leads it; a point's group index is its leader's rank
+        // among the leaders.  Misses belong to no group.
         const int v_own = __float_as_int(lt[48 + own]);
-        const int v_prev = __float_as_int(lt[48 + prev]);
-        const uint32_t bmask = __ballot_sync(kFull, (lane & 15) == 0 || v_own != v_prev) & 0xFFFFu;
-        const uint32_t anyhit = __ballot_sync(kFull, v_own >= 0);
-        if (anyhit == 0) continue;
+        const uint32_t same = __match_any_sync(kFull, v_own);
+        const int lead = __ffs(same) - 1;
+        const uint32_t bmask = __ballot_sync(kFull, v_own >= 0 && lead == lane);      // leaders (all in lanes 0..15)
+        if (bmask == 0) continue;
+        const int rid_own = v_own >= 0 ? __popc(bmask & ((1u << lead) - 1u)) : 255;
         const shine_level& lv = P.oct.lv[i];
         const int32_t* slot_words = reinterpret_cast<const int32_t*>(lv.hash_slots);
         float* gb = grad_base(lv, (uint32_t)tile, kF);
@@ -449,17 +451,16 @@ __device__ __forceinline__ void grouped_scatter(const StepParams& P, int L, int 
             f2_unpack(f2_mul(f2_mul(X01, Y01), Z01), w[0], w[1]);
             f2_unpack(f2_mul(f2_mul(X23, Y23), Z23), w[2], w[3]);
         }
-        // run index of those four points
+        // group index of those four points
         int rid[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) rid[q] = __popc(bmask & ((2u << (t + 4 * q)) - 1u)) - 1;
+        for (int q = 0; q < 4; ++q) rid[q] = __shfl_sync(kFull, rid_own, t + 4 * q);
         uint32_t rem = bmask;
         for (int r = 0; r < nruns; r += 2) {
             const int p1 = __ffs(rem) - 1; rem &= rem - 1;
             const int p2 = rem ? __ffs(rem) - 1 : p1; rem &= rem - 1;     // odd run count: the last pass has one run only
             const int v1 = __shfl_sync(kFull, v_own, p1);
             const int v2 = (r + 1 < nruns) ? __shfl_sync(kFull, v_own, p2) : -1;
-            if (v1 < 0 && v2 < 0) continue;                              // runs of misses
             AFrag<3> a0, a1;     // rows g: run r, rows g + 8: run r + 1; k = points of chunk 0 / chunk 1
             a0.set(rid[0] == r ? w[0] : 0.f, rid[0] == r + 1 ? w[0] : 0.f, rid[1] == r ? w[1] : 0.f, rid[1] == r + 1 ? w[1] : 0.f);
             a1.set(rid[2] == r ? w[2] : 0.f, rid[2] == r + 1 ? w[2] : 0.f, rid[3] == r ? w[3] : 0.f, rid[3] == r + 1 ? w[3] : 0.f);
@@ -481,6 +482,7 @@ __device__ __forceinline__ void grouped_scatter(const StepParams& P, int L, int 
 template <int NTF, bool TRAIN, bool DEC_GRAD, int LMAX, bool GROUPED = false>
 __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MINB) sdf_fused_kernel(const __grid_constant__ StepParams P) {
     static_assert(!GROUPED || TRAIN, "the grouped scatter belongs to the training kernels");
+    static_assert(SmemPlan::kStagePerWarp >= SmemPlan::kDecGradFloats, "a warp's staging area holds its partial decoder gradient");
     extern __shared__ __align__(16) float smem[];
     uint32_t* smu = reinterpret_cast<uint32_t*>(smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -506,7 +508,6 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         smem[SmemPlan::W3 + tid] = P.dec.w3[tid];
     }
     if (tid == 0) smem[SmemPlan::B3] = P.dec.b3 ? P.dec.b3[0] : 0.f;
-    if (DEC_GRAD) for (int i = tid; i < 1380; i += blockDim.x) smem[SmemPlan::RED + i] = 0.f;
     // Tensor-Memory parking areas of this warp (lanes 32*(warp&3).., column group warp>>2):
     //   tpark: per-tile state that must survive the MLP phase (blend factors tx,ty,tz of every level + slot indices)
     //   tacc : decoder-gradient accumulators (DEC_GRAD only)
@@ -1110,21 +1111,21 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
     if (DEC_GRAD) {
         SHINE_ACC_DECL;
         SHINE_ACC_LOAD(tacc);
-        float* red = smem + SmemPlan::RED;   // [gw1 256 | gb1 32 | gw2 1024 | gb2 32 | gw3 32 | gb3 1]
+        // every warp writes its complete partial gradient vector [gw1 256 | gb1 32 | gw2 1024 | gb2 32 | gw3 32 | gb3 1]
+        // into its own staging area (each element has exactly one owner lane: plain stores, no shared-memory atomics),
+        // then the block sums the eight vectors and issues one global atomic per non-zero element
+        float* part = stage;
         constexpr int oW1 = 0, oB1 = 256, oW2 = 288, oB2 = 1312, oW3 = 1344, oB3 = 1376;
+        __syncwarp();
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
-                atomicAdd(red + oW2 + (16 * mt + g) * kH + 8 * nt + 2 * t, dW2[mt][nt][0]);
-                atomicAdd(red + oW2 + (16 * mt + g) * kH + 8 * nt + 2 * t + 1, dW2[mt][nt][1]);
-                atomicAdd(red + oW2 + (16 * mt + g + 8) * kH + 8 * nt + 2 * t, dW2[mt][nt][2]);
-                atomicAdd(red + oW2 + (16 * mt + g + 8) * kH + 8 * nt + 2 * t + 1, dW2[mt][nt][3]);
+                *reinterpret_cast<float2*>(part + oW2 + (16 * mt + g) * kH + 8 * nt + 2 * t) = make_float2(dW2[mt][nt][0], dW2[mt][nt][1]);
+                *reinterpret_cast<float2*>(part + oW2 + (16 * mt + g + 8) * kH + 8 * nt + 2 * t) = make_float2(dW2[mt][nt][2], dW2[mt][nt][3]);
             }
-            atomicAdd(red + oW1 + (16 * mt + g) * kF + 2 * t, dW1[mt][0]);
-            atomicAdd(red + oW1 + (16 * mt + g) * kF + 2 * t + 1, dW1[mt][1]);
-            atomicAdd(red + oW1 + (16 * mt + g + 8) * kF + 2 * t, dW1[mt][2]);
-            atomicAdd(red + oW1 + (16 * mt + g + 8) * kF + 2 * t + 1, dW1[mt][3]);
+            *reinterpret_cast<float2*>(part + oW1 + (16 * mt + g) * kF + 2 * t) = make_float2(dW1[mt][0], dW1[mt][1]);
+            *reinterpret_cast<float2*>(part + oW1 + (16 * mt + g + 8) * kF + 2 * t) = make_float2(dW1[mt][2], dW1[mt][3]);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -1140,18 +1141,20 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                     a += __shfl_xor_sync(kFull, a, o); b += __shfl_xor_sync(kFull, b, o); c += __shfl_xor_sync(kFull, c, o);
                 }
                 if (g == 0) {
-                    atomicAdd(red + oB1 + 8 * j + 2 * t + q, a);
-                    atomicAdd(red + oB2 + 8 * j + 2 * t + q, b);
-                    atomicAdd(red + oW3 + 8 * j + 2 * t + q, c);
+                    part[oB1 + 8 * j + 2 * t + q] = a;
+                    part[oB2 + 8 * j + 2 * t + q] = b;
+                    part[oW3 + 8 * j + 2 * t + q] = c;
                 }
             }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) db3p += __shfl_xor_sync(kFull, db3p, o);
-        if (lane == 0) atomicAdd(red + oB3, db3p);
+        if (lane == 0) part[oB3] = db3p;
         __syncthreads();
         for (int i = tid; i < SmemPlan::kDecGradFloats; i += blockDim.x) {
-            const float v = red[i];
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) v += smem[SmemPlan::STAGE + w * SmemPlan::kStagePerWarp + i];
             if (v == 0.f) continue;
             float* dst;
             if (i < oB1) dst = P.dec.gw1 + i;

@@ -5,11 +5,12 @@
 // (shine_boundary_pack -> ncclAllReduce -> shine_boundary_unpack) is three launches and ~20 us of collective latency; here
 // every rank runs one small kernel:
 //     1. pack      own decoder segment + own boundary rows -> own exchange buffer (parity = step & 1)
-//     2. publish   last block to finish: __threadfence_system, then store the step number into its flag slot in EVERY
-//                  peer's buffer (plain stores through the peers' IPC-mapped pointers)
+//     2. publish   last block to finish: release-store (system scope) of the step number into its flag slot in EVERY
+//                  peer's buffer, through the peers' IPC-mapped pointers
 //     3. wait      until every peer's flag in the local buffer has reached the step number (bounded spin)
-//     4. reduce    out[i] = sum over ranks 0..n-1 (fixed order: bitwise identical on every rank) of the peers' buffers,
-//                  read straight over NVLink, written in place into the decoder gradients / the table-gradient rows
+//     4. reduce    out[i] = sum over the ranks that hold a row of the corner (fixed order: bitwise identical on every rank)
+//                  of their buffers, read straight over NVLink with all of a thread's loads in flight together, written
+//                  in place into the decoder gradients / the table-gradient rows
 // Double buffering by step parity replaces the trailing barrier: a rank can only overwrite parity p two steps later, and
 // it cannot get there before every peer has published the step in between, i.e. has finished reading parity p.
 // Buffers are cudaMalloc'ed here and shared with cudaIpc*MemHandle (one process per GPU).
@@ -56,7 +57,9 @@ __device__ __forceinline__ float4 ld_peer_f4(const float* p) {
     return v;
 }
 
-__global__ void __launch_bounds__(1024) p2p_exchange_kernel(const __grid_constant__ P2PParams P) {
+constexpr int kP2PThreads = 512;
+
+__global__ void __launch_bounds__(kP2PThreads) p2p_exchange_kernel(const __grid_constant__ P2PParams P) {
     unsigned char* mine_base = P.peer[P.rank];
     float* mine = data_of(mine_base, P.step, P.max_floats);
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gs = (int64_t)gridDim.x * blockDim.x;
@@ -84,16 +87,42 @@ __global__ void __launch_bounds__(1024) p2p_exchange_kernel(const __grid_constan
         if (threadIdx.x == 0) {
             __threadfence();
             const uint32_t prev = atomicAdd(const_cast<uint32_t*>(ctrl), 1u);
+            __threadfence();                                              // acquire side of the hand-shake for the last block
             is_last = prev == gridDim.x - 1;
             if (is_last) ctrl[0] = 0u;                                    // ready for the next launch
         }
         __syncthreads();
     }
-    if (is_last && threadIdx.x < P.nranks) {
-        __threadfence_system();
+    if (is_last && threadIdx.x < P.nranks) {        // st.release.sys orders everything the barrier made visible to this thread
         uint32_t* flag = reinterpret_cast<uint32_t*>(P.peer[threadIdx.x] + (size_t)P.rank * kFlagStride);
         asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(P.step) : "memory");
     }
+    // while the publication travels: which of this thread's exchange-buffer quads does the rank hold, and which ranks
+    // contribute to them (local reads only).  Up to kItems quads per thread; the launch sizes the grid so that this covers
+    // the buffer, the tail loop below catches anything beyond.
+    constexpr int kItems = 2;
+    float* dst[kItems];
+    uint32_t from[kItems];
+    const int64_t n4 = P.total_floats / 4;
+    const uint32_t everyone = P.nranks >= 32 ? 0xFFFFFFFFu : ((1u << P.nranks) - 1u);
+    auto locate = [&](int64_t i, float*& d, uint32_t& m) {
+        d = nullptr; m = 0u;
+        if (i >= n4) return;
+        const int64_t fo = 4 * i;                                    // float offset in the exchange buffer
+        if (fo < P.dec_floats) { d = P.dec + fo; m = everyone; return; }
+        int l = 0;
+#pragma unroll
+        for (int q = 1; q < SHINE_MAX_LEVELS; ++q)
+            if (q < P.num_levels && fo >= P.plan.lv[q].offset) l = q;
+        const int64_t rel = fo - P.plan.lv[l].offset;
+        const int slot = (int)(rel / P.feature_dim), within = (int)(rel % P.feature_dim);
+        const int row = P.inv.row_of_slot[l][slot];
+        if (row < 0) return;                                         // a corner this rank does not hold
+        d = P.plan.lv[l].table + (int64_t)row * P.feature_dim + within;
+        m = P.inv.holders[l] ? (uint32_t)P.inv.holders[l][slot] : everyone;
+    };
+#pragma unroll
+    for (int k = 0; k < kItems; ++k) locate(gt + k * gs, dst[k], from[k]);
     // 3. wait for every rank's publication of this step (acquire loads of the local flags the peers write)
     if (threadIdx.x < P.nranks) {
         const uint32_t* flag = reinterpret_cast<const uint32_t*>(mine_base + (size_t)threadIdx.x * kFlagStride);
@@ -105,31 +134,56 @@ __global__ void __launch_bounds__(1024) p2p_exchange_kernel(const __grid_constan
         } while ((int32_t)(seen - P.step) < 0);
     }
     __syncthreads();
-    // 4. reduce, fixed rank order, in place.  ONE flat loop over [decoder | level 0 slots | level 1 slots | ...]: every
-    //    NVLink load of a pass is independent of every other (per-level loops would serialise one round trip per level)
-    const int64_t n4 = P.total_floats / 4;
-    for (int64_t i = gt; i < n4; i += gs) {
-        const int64_t fo = 4 * i;                                    // float offset in the exchange buffer
-        float* dst = nullptr;
-        if (fo < P.dec_floats) {
-            dst = P.dec + fo;
-        } else {
-            int l = 0;
-#pragma unroll
-            for (int q = 1; q < SHINE_MAX_LEVELS; ++q)
-                if (q < P.num_levels && fo >= P.plan.lv[q].offset) l = q;
-            const int64_t rel = fo - P.plan.lv[l].offset;
-            const int slot = (int)(rel / P.feature_dim), within = (int)(rel % P.feature_dim);
-            const int row = P.inv.row_of_slot[l][slot];
-            if (row >= 0) dst = P.plan.lv[l].table + (int64_t)row * P.feature_dim + within;
-        }
-        if (!dst) continue;                                            // a corner this rank does not hold
+    // 4. reduce in place, fixed rank order (bitwise identical on every rank).  Only the ranks that hold a row of the corner
+    //    are read, and all of a thread's NVLink loads are in flight together: one round trip, not one per rank.
+    auto reduce_item = [&](int64_t i, float* d, uint32_t m) {
+        const int64_t fo = 4 * i;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < P.nranks; ++r) {
-            const float4 v = ld_peer_f4(data_of(P.peer[r], P.step, P.max_floats) + fo);
-            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+#pragma unroll
+        for (int base = 0; base < kMaxRanks; base += 8) {
+            if (base >= P.nranks) break;
+            float4 v[8];
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (base + r < P.nranks && ((m >> (base + r)) & 1u))
+                    v[r] = ld_peer_f4(data_of(P.peer[base + r], P.step, P.max_floats) + fo);
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
         }
-        *reinterpret_cast<float4*>(dst) = acc;
+        *reinterpret_cast<float4*>(d) = acc;
+    };
+    if (kItems == 2 && dst[0] && dst[1] && P.nranks <= 8) {
+        // both quads of this thread: sixteen loads in flight
+        float4 va[8], vb[8];
+        const int64_t fa = 4 * gt, fb = 4 * (gt + gs);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            va[r] = make_float4(0.f, 0.f, 0.f, 0.f); vb[r] = va[r];
+            if (r < P.nranks) {
+                const float* base = data_of(P.peer[r], P.step, P.max_floats);
+                if ((from[0] >> r) & 1u) va[r] = ld_peer_f4(base + fa);
+                if ((from[1] >> r) & 1u) vb[r] = ld_peer_f4(base + fb);
+            }
+        }
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            a.x += va[r].x; a.y += va[r].y; a.z += va[r].z; a.w += va[r].w;
+            b.x += vb[r].x; b.y += vb[r].y; b.z += vb[r].z; b.w += vb[r].w;
+        }
+        *reinterpret_cast<float4*>(dst[0]) = a;
+        *reinterpret_cast<float4*>(dst[1]) = b;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kItems; ++k)
+            if (dst[k]) reduce_item(gt + k * gs, dst[k], from[k]);
+    }
+    for (int64_t i = gt + kItems * gs; i < n4; i += gs) {             // buffers beyond kItems quads per thread
+        float* d; uint32_t m;
+        locate(i, d, m);
+        if (d) reduce_item(i, d, m);
     }
 }
 
@@ -197,6 +251,7 @@ int shine_p2p_exchange(shine_p2p* ctx, float* dec_grads, int64_t dec_floats, con
         end += (int64_t)inverse->slots[l] * feature_dim;
         P.plan.lv[l] = b;
         P.inv.row_of_slot[l] = inverse->row_of_slot[l]; P.inv.slots[l] = inverse->slots[l];
+        P.inv.holders[l] = inverse->holders[l];
     }
     if (end > ctx->max_floats) return SHINE_ERR_INVALID_ARG;
     P.total_floats = end;
@@ -207,10 +262,12 @@ int shine_p2p_exchange(shine_p2p* ctx, float* dec_grads, int64_t dec_floats, con
     P.nranks = ctx->nranks; P.rank = ctx->rank; P.step = ctx->step; P.max_floats = ctx->max_floats; P.dec_floats = dec_floats;
     P.dec = dec_grads; P.num_levels = num_levels; P.feature_dim = feature_dim;
     DeviceGuard guard(ctx->local);
-    // latency-bound for the usual few KB: one block (no grid hand-shake); more blocks only for big boundary sets
-    int64_t blocks = most <= 16 * 1024 ? 1 : (most + 8191) / 8192;
-    if (blocks > 32) blocks = 32;
-    p2p_exchange_kernel<<<(unsigned)blocks, 1024, 0, (cudaStream_t)stream>>>(P);
+    // latency-bound: every thread should own at most two quads of the buffer, so that the reduce is ONE NVLink round trip
+    // (the step kernel has retired: all SMs are free).  One block (no grid hand-shake) covers 1 024 quads = 16 KB.
+    int64_t blocks = (most + 2 * kP2PThreads - 1) / (2 * kP2PThreads);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 128) blocks = 128;
+    p2p_exchange_kernel<<<(unsigned)blocks, kP2PThreads, 0, (cudaStream_t)stream>>>(P);
     return (int)cudaGetLastError();
 }
 

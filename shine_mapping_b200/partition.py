@@ -61,6 +61,7 @@ class BoundaryPlan:
         self.rank, self.world, self.feature_dim = rank, world, feature_dim
         self.dec_floats = dec_floats
         self.rows, self.slots, self.owned, self.counts, self.offsets, self.inverse = [], [], [], [], [], []
+        self.holders = []                  # per level, per shared corner: bit r set <=> rank r holds a row of it
         off = dec_floats
         for lvl in range(n_levels):        # coarse -> fine, like hier_features
             keys_all = torch.cat([per_rank_level_keys[r][lvl].cpu() for r in range(world)])
@@ -77,6 +78,9 @@ class BoundaryPlan:
             first = torch.full((uniq.numel(),), world, dtype=torch.int64)
             first.scatter_reduce_(0, inv, ranks_all, reduce="amin")
             owner_of_shared = first[cnt > 1]
+            held = torch.zeros(uniq.numel(), dtype=torch.int64)
+            held.scatter_add_(0, inv, torch.ones_like(ranks_all) << ranks_all)   # a rank lists a key once: sum == or
+            self.holders.append(held[cnt > 1].to(torch.int32))
             inv = torch.full((int(shared.numel()),), -1, dtype=torch.int32)
             inv[slots] = rows.to(torch.int32)
             self.inverse.append(inv)
@@ -92,6 +96,7 @@ class BoundaryPlan:
         self.slots = [t.to(device) for t in self.slots]
         self.owned = [t.to(device) for t in self.owned]
         self.inverse = [t.to(device) for t in self.inverse]
+        self.holders = [t.to(device) for t in self.holders]
         return self
 
     def inverse_descriptor(self) -> _abi.ShineBoundaryInverse:
@@ -99,6 +104,7 @@ class BoundaryPlan:
         for lvl, inv in enumerate(self.inverse):
             d.row_of_slot[lvl] = inv.data_ptr() if inv.numel() else None
             d.slots[lvl] = int(inv.numel())
+            d.holders[lvl] = self.holders[lvl].data_ptr() if inv.numel() else None
         return d
 
     def descriptor(self, tables, buf_base_offset: int = 0) -> _abi.ShineBoundary:

@@ -132,7 +132,10 @@ class SdfTrainer:
                 (_abi.FLAG_TCGEN05 if self.tcgen05 else 0) | \
                 (_abi.FLAG_MORTON_ORDERED if (self.morton_ordered if morton_ordered is None else morton_ordered) else 0)
         scale = 1.0 if cfg.loss_reduction == "sum" else 1.0 / float(n_norm if n_norm else n)
-        od = self.octree._descriptor(None, self.table_grads, n_points=n if self.use_replicas else 0)
+        # gradient replicas spread same-row atomics of unordered batches; the grouped scatter of ordered batches issues one
+        # red per run and row, so it goes straight to the gradient table (and there is no fold kernel)
+        replicas = self.use_replicas and not (flags & _abi.FLAG_MORTON_ORDERED)
+        od = self.octree._descriptor(None, self.table_grads, n_points=n if replicas else 0)
         dd = self.decoder.c_descriptor(self.dec_grads if self._dec_trainable else None)
         if not accumulate_loss and not self._loss_clean:
             self.loss.zero_()
@@ -143,7 +146,7 @@ class SdfTrainer:
             _abi.ptr(pred_out), _abi.ptr(self.loss), flags, _abi.stream_ptr(coord.device)), "shine_sdf_bce_step")
         if mid_event is not None:          # lets a profiler time the fused kernel and the replica fold separately
             mid_event.record()
-        if self.use_replicas:
+        if replicas:
             self.octree._reduce_replicas(od, coord.device)
         return self.loss
 

@@ -54,6 +54,27 @@ def test_balanced_bounds_partition_every_sample_once():
                 assert int(k.min()) >= int(bounds[r]) and int(k.max()) < int(bounds[r + 1])
 
 
+def test_holder_masks_name_exactly_the_ranks_that_list_a_shared_corner():
+    """BoundaryPlan.holders (what the peer-memory exchange reads instead of every rank's buffer): bit r of a slot's
+    mask <=> rank r's plan lists that slot; every mask has >= 2 bits; all ranks agree on the masks."""
+    cfg, pool, batch, dec = global_scene()
+    world = 3
+    _, _, _, plans = _rank_setup(cfg, pool, batch, world)
+    for lvl in range(len(plans[0].counts)):
+        masks = plans[0].holders[lvl].long()
+        assert masks.numel() == plans[0].counts[lvl]
+        for p in plans[1:]:
+            assert torch.equal(p.holders[lvl].long(), masks)
+        want = torch.zeros_like(masks)
+        for r, p in enumerate(plans):
+            want[p.slots[lvl].long()] |= 1 << r
+            assert torch.equal(p.inverse[lvl][p.slots[lvl].long()].long(), p.rows[lvl].long())
+        assert torch.equal(want, masks)
+        if masks.numel():
+            bits = sum(((masks >> r) & 1) for r in range(world))
+            assert int(bits.min()) >= 2
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_partitioned_step_equals_single_process_step(world):
     """Sum over ranks of (local step on the rank's share of a fixed global batch) + boundary exchange == the single
