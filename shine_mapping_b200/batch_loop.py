@@ -93,8 +93,11 @@ class _GraphedIteration:
         self.graph, self.lr = None, None
 
     def _body(self):
-        coord, sdf_label, weight = self.pool.get_batch(self.bs)
-        if self.trainer.config.ekional_loss_on:
+        # the eikonal kernel scatters per point: it wants the order drawn (Morton order = same-row atomics within a warp)
+        eik = self.trainer.config.ekional_loss_on
+        kw = {"ordered": False} if (eik and getattr(self.pool, "ordered", False)) else {}
+        coord, sdf_label, weight = self.pool.get_batch(self.bs, **kw)
+        if eik:
             self.trainer.forward_backward_eikonal(coord, sdf_label, weight)
         else:
             self.trainer.forward_backward(coord, sdf_label, weight, morton_ordered=getattr(self.pool, "ordered", False))
@@ -143,7 +146,7 @@ def run_shine_mapping_batch(config: SHINEConfig, octree: FeatureOctree, decoder:
         if graphed is not None:
             graphed.run()
         elif config.ekional_loss_on:
-            coord, sdf_label, weight = pool.get_batch(config.bs)
+            coord, sdf_label, weight = pool.get_batch(config.bs, **({"ordered": False} if getattr(pool, "ordered", False) else {}))
             trainer.forward_backward_eikonal(coord, sdf_label, weight, n_norm=config.bs * world)
             trainer.all_reduce_grads()
             trainer.optimizer_step(zero_grad=True)

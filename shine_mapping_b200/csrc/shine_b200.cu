@@ -584,6 +584,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
     // walk below hit L1 and only the row gather pays an L2 round trip
     unsigned long long skey0 = 0ull;
     int smine[LMAX / 2];
+    uint4 skf[LMAX / 2];
 #pragma unroll
     for (int j = 0; j < LMAX / 2; ++j) smine[j] = -1;
     auto stage_slots = [&](bool v, float sx, float sy, float sz) {
@@ -596,9 +597,13 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                 const shine_level& lv = P.oct.lv[i];
                 const unsigned long long kq = consecutive ? (skey0 >> (3 * i)) : morton_of(sx, sy, sz, lv.level);
                 smine[j] = (int)(hash_key(kq) & (lv.hash_capacity - 1));
-                const char* sp = reinterpret_cast<const char*>(reinterpret_cast<const HashSlot*>(lv.hash_slots) + smine[j]);
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(sp));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(sp + 32));
+                const HashSlot* sp = reinterpret_cast<const HashSlot*>(lv.hash_slots) + smine[j];
+                if (SHINE_SLOT_PREFETCH == 2) {          // the home-slot load itself is issued a scatter phase early
+                    skf[j] = __ldg(reinterpret_cast<const uint4*>(sp));
+                } else {
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(sp));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(reinterpret_cast<const char*>(sp) + 32));
+                }
             }
         }
     };
@@ -753,7 +758,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                     const HashSlot* slots = reinterpret_cast<const HashSlot*>(lv.hash_slots);
                     kq[j] = consecutive ? (key0 >> (3 * i)) : morton_of(x, y, z, lv.level);
                     mine[j] = kSlotPrefetch ? smine[j] : (int)(hash_key(kq[j]) & (lv.hash_capacity - 1));
-                    kf[j] = __ldg(reinterpret_cast<const uint4*>(slots + mine[j]));
+                    kf[j] = (kSlotPrefetch && SHINE_SLOT_PREFETCH == 2) ? skf[j] : __ldg(reinterpret_cast<const uint4*>(slots + mine[j]));
                 }
             }
 #pragma unroll

@@ -29,6 +29,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_abi.ShineOctree) == 16 + 8 * 48
     assert C.sizeof(_abi.ShineDecoder) == 12 * 8 + 16
     assert C.sizeof(_abi.ShineAdamTensor) == 48
+    assert C.sizeof(_abi.ShineBoundaryInverse) == 8 * 8 + 8 * 4 + 8 * 8      # row_of_slot | slots | holders (SHINE_MAX_LEVELS = 8)
 
 
 def test_abi_argument_checks_need_no_gpu(built_lib):
@@ -208,3 +209,35 @@ def test_synth_sampler_contract():
     # label is the signed displacement along the ray: |coord - hit| == |label|
     disp = torch.linalg.norm(coord.reshape(-1, 6, 3) - (hits * cfg.scale).unsqueeze(1), dim=2)
     assert torch.allclose(disp, label.reshape(-1, 6).abs(), atol=2e-7)
+
+
+def test_sample_pool_morton_order_keeps_the_sampler_and_orders_the_batch():
+    """SamplePool.sort_morton(): same samples, Z-order; get_batch() then draws the same randint index stream as before and
+    hands the samples out in ascending index = Morton order (a subsequence of a Morton-ordered sequence is Morton-ordered);
+    ordered=False gives the order drawn; an unsorted pool refuses ordered=True."""
+    from shine_mapping_b200 import synth
+    from shine_mapping_b200.feature_octree import points_to_morton, quantize_points
+    g = torch.Generator().manual_seed(3)
+    pool = synth.SamplePool("cpu")
+    coord = torch.rand(5000, 3, generator=g) * 1.6 - 0.8
+    pool.append(coord, torch.arange(5000, dtype=torch.float32), torch.ones(5000))
+    with pytest.raises(ValueError):
+        pool.get_batch(10, ordered=True)
+    assert pool.ordered is False
+    pool.sort_morton()
+    assert pool.ordered and len(pool) == 5000
+    keys = points_to_morton(quantize_points(pool.coord_pool, 16))
+    assert bool((keys[1:] >= keys[:-1]).all())
+    assert torch.equal(torch.sort(pool.sdf_label_pool).values, torch.arange(5000, dtype=torch.float32))   # a permutation
+    assert torch.equal(pool.coord_pool, coord[pool.sdf_label_pool.long()])                                 # rows moved together
+    c, l, w = pool.get_batch(700, torch.Generator().manual_seed(9))
+    bk = points_to_morton(quantize_points(c, 16))
+    assert bool((bk[1:] >= bk[:-1]).all())
+    for lvl in (12, 9):          # ordered at every coarser level too (Morton prefixes)
+        ck = points_to_morton(quantize_points(c, lvl))
+        assert bool((ck[1:] >= ck[:-1]).all())
+    c2, l2, _ = pool.get_batch(700, torch.Generator().manual_seed(9), ordered=False)
+    assert torch.equal(torch.sort(l).values, torch.sort(l2).values)          # the same index multiset, another order
+    assert not torch.equal(l, l2)
+    pool.append(coord[:3], torch.zeros(3), torch.ones(3))
+    assert pool.ordered is False                                              # appending breaks the order until re-sorted
