@@ -117,10 +117,12 @@ BATCH_ORDER_NOTE = {
     "random": "randint-drawn samples in the order drawn (the reference's order)"}
 
 
-def shared_config(cfg, n_azimuth, pool_len, n, world, rows, batch_order="morton"):
+def shared_config(cfg, n_azimuth, pool_len, n, world, rows, batch_order="morton", l2="rotate"):
     """The `config` object of the JSON line — identical for our arm and the reference arm (same workload, same N)."""
     return {"workload": cfg.name, "n_azimuth": n_azimuth, "pool_samples": pool_len, "points_per_step_per_gpu": n,
             "batch_order": batch_order, "batch_order_note": BATCH_ORDER_NOTE[batch_order],
+            "l2_rule": "inputs larger than L2 (timed steps rotate over batches that together exceed it; GPU arm)" if l2 == "rotate"
+                       else "L2 flushed before every timed step (GPU arm)",
             "global_points_per_step": n * world, "tree_level_feat": L, "feature_dim": F, "table_rows": rows,
             "decoder": "geo_decoder_8dim arch 8-32-32-1, trainable", "loss": "sdf_bce mean",
             "step": "grad zero + fwd + loss + bwd (table scatter-add + decoder grads); no optimizer"}
@@ -259,7 +261,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": shared_config(cfg, args.n_azimuth, len(pool), n, max(args.gpus, 1),
-                                [int(p.shape[0]) for p in octree.hier_features], args.batch_order),
+                                [int(p.shape[0]) for p in octree.hier_features], args.batch_order, args.l2),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{sample} randint-drawn samples of the {len(pool)}-sample C2 scan per step "
                                    f"(= the points_per_step_per_gpu of our arm)" if sample == n else
@@ -301,12 +303,23 @@ def e2e_record(n, n_global, pipe_sec, sync_sec, n_host, loss_last):
     return rec
 
 
+L2_BYTES = 126 << 20
+
+
+def batches_exceeding_l2(n_points, cap=64):
+    """How many distinct device batches (16 B per point) it takes to exceed the L2 by 1.6x; None if more than `cap`."""
+    need = -(-int(1.6 * L2_BYTES) // max(1, n_points * 16))
+    return max(4, need) if need <= cap else None
+
+
 def time_steps(trainer, batches, steps, flush_buf, n_norm, dev, all_reduce=True):
-    """K steps with the L2 flushed before each; -> per-step (zero+kernel+reduce+allreduce), fused kernel alone, replica
+    """K steps; flush_buf given: the L2 is flushed before each (untimed 256 MiB write), None: the batches rotate and are
+    together larger than L2.  -> per-step (zero+kernel+reduce+allreduce), fused kernel alone, replica
     reduce alone, in ms (means).  CUDA events on the launching stream."""
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(steps)]
     for k in range(steps):
-        flush_buf.fill_(k & 0xFF)                     # > L2 (126 MB): evicts tables, inputs and gradients
+        if flush_buf is not None:
+            flush_buf.fill_(k & 0xFF)                 # > L2 (126 MB): evicts tables, inputs and gradients
         b = batches[k % len(batches)]
         ev[k][0].record()
         trainer.zero_grad()
@@ -542,8 +555,18 @@ def run_ours(args):
         pool.sort_morton()      # once, with the map; batches are then handed out in Morton order
     n_global = n * world
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
-    batches = [pool.get_batch(n, gen) for _ in range(4)]
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    # L2 rule: inputs larger than L2 (default) -- the timed steps rotate over batches that together exceed the 126 MB L2 by
+    # 1.6x, so every step streams its inputs from HBM while the persistent state (tables, gradients, exchange plan) stays
+    # resident exactly as it does in a training run; `--l2 flush` evicts everything before every step instead.
+    n_rot = batches_exceeding_l2(n) if args.l2 == "rotate" else None
+    rotate = n_rot is not None
+    batches = [pool.get_batch(n, gen) for _ in range(n_rot if rotate else 4)]
+    nb = len(batches)
+    flush_all = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_buf = None if rotate else flush_all
+    l2_note = (f"inputs larger than L2: the timed steps rotate over {nb} batches = {nb * n * 16 / 2**20:.0f} MiB (L2 126 MiB); "
+               "tables and gradients stay resident as in training" if rotate else
+               "flushed between timed steps (256 MiB write, not timed)")
 
     def step(b):
         trainer.zero_grad()
@@ -551,8 +574,8 @@ def run_ours(args):
         trainer.all_reduce_grads()
 
     warm = max(args.warmup, 3)
-    for i in range(warm):
-        step(batches[i % 4])
+    for i in range(max(warm, nb if rotate else 0)):
+        step(batches[i % nb])
     torch.cuda.synchronize(dev)
 
     # ---- `value`: inputs resident in HBM, CUDA events on the launching stream, L2 flushed between steps ----
@@ -576,7 +599,7 @@ def run_ours(args):
     other_order = None
     if world == 1 and ordered:      # the same step on batches in the order drawn (general kernel), for the record
         tr_r = SdfTrainer(cfg, octree, decoder, shard_mode="spatial", morton_ordered=False)
-        br = [pool.get_batch(n, gen, ordered=False) for _ in range(2)]
+        br = [pool.get_batch(n, gen, ordered=False) for _ in range(nb if rotate else 2)]
         for i in range(3):
             tr_r.zero_grad(); tr_r.forward_backward(br[i % 2][0], br[i % 2][1], None, n_norm=n_global)
         r_step, r_kern, _ = time_steps(tr_r, br, args.steps, flush_buf, n_global, dev)
@@ -584,6 +607,11 @@ def run_ours(args):
                        "kernel_ms": r_kern, "kernel": "sdf_fused_kernel<3,train,dec_grad,4> (per-point reds)",
                        "note": BATCH_ORDER_NOTE["random"]}
         del tr_r, br
+    flushed = None
+    if world == 1 and rotate:       # the conservative variant, for the record: everything evicted before every step
+        f_step, f_kern, _ = time_steps(trainer, batches, args.steps, flush_all, n_global, dev)
+        flushed = {"value": n_global / (f_step * 1e-3), "ms_per_step": f_step, "kernel_ms": f_kern,
+                   "l2": "flushed between timed steps (256 MiB write, not timed): tables and gradients come from HBM too"}
     exch_ms_max = sdist.max_over_ranks(exch_ms, dev)
     exch_ms_min = -sdist.max_over_ranks(-exch_ms, dev)
     kern_ms_min = -sdist.max_over_ranks(-kern_ms, dev)
@@ -592,7 +620,7 @@ def run_ours(args):
     # number of collectives.
     n_cont = max(0, min(20000, int(500.0 / max(step_ms, 0.02)) - args.steps))
     for k in range(n_cont):
-        step(batches[k % 4])
+        step(batches[k % nb])
         if k % 64 == 63:
             torch.cuda.synchronize(dev)
     torch.cuda.synchronize(dev)
@@ -626,7 +654,8 @@ def run_ours(args):
     sync_ts = []
     sdist.barrier(dev); torch.cuda.synchronize(dev)
     for k in range(args.steps):
-        flush_buf.fill_(k & 0xFF)
+        if flush_buf is not None:
+            flush_buf.fill_(k & 0xFF)
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
         trainer.step_from_host(*host[k % n_host])     # ends with loss.item(): device -> host read
@@ -637,7 +666,7 @@ def run_ours(args):
 
     if rank != 0:
         return
-    del flush_buf
+    del flush_buf, flush_all
     peak, peak_src = peaks()
     cnt = kernel_counters()
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
@@ -651,7 +680,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": shared_config(cfg, args.n_azimuth, len(pool), n, world, rows, args.batch_order),
+        "config": shared_config(cfg, args.n_azimuth, len(pool), n, world, rows, args.batch_order,
+                                args.l2 if rotate else "flush"),
         "impl_notes": {"decoder_math": "3xTF32 mma.sync (fp32-grade)",
                        "other_batch_order": other_order,
                        "parallelism": "single GPU" if world == 1 else
@@ -661,7 +691,7 @@ def run_ours(args):
                        "exchange_ms": {"max_over_ranks": exch_ms_max, "min_over_ranks": exch_ms_min,
                                        "note": "events around the exchange: its latency + the wait for the slowest rank's kernel"},
                        "kernel_ms_min_over_ranks": kern_ms_min,
-                       "l2": "flushed between timed steps (256 MiB write, not timed)",
+                       "l2": l2_note, "l2_flushed": flushed,
                        "timed_step": "grad memset + fused fwd+loss+bwd kernel + replica fold (+ all-reduce when N>1)"},
         # the C2 map (2.75 MB of features) lives in L2: the kernel's physical bound there is the L1TEX LSU data pipe
         # (1 wavefront / clk / SM), not HBM.  wavefronts/point come from the committed ncu capture, time is live.
@@ -725,6 +755,8 @@ def main():
                     help="N>1: the step's exchange — NCCL all-reduce through the C ABI, or the one-kernel NVLink peer-memory path")
     ap.add_argument("--batch-order", default="morton", choices=["morton", "random"],
                     help="order the sampler hands a batch out in (same random index multiset either way)")
+    ap.add_argument("--l2", default="rotate", choices=["rotate", "flush"],
+                    help="L2 rule of the timed steps: rotate over batches that together exceed L2 (default) or flush before every step")
     ap.add_argument("--no-hbm-leg", action="store_true")
     ap.add_argument("--hbm-only", action="store_true", help="run only the HBM-bound leg and print its object (ncu target)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
