@@ -48,9 +48,9 @@ def _oracle_with_tables(octree, decoder, own_update_from=None):
     return o, dec
 
 
-def _cuda_step(cfg, octree, decoder, coord, label):
+def _cuda_step(cfg, octree, decoder, coord, label, morton_ordered=False):
     from shine_mapping_b200 import SdfTrainer
-    tr = SdfTrainer(cfg, octree, decoder)
+    tr = SdfTrainer(cfg, octree, decoder, morton_ordered=morton_ordered)
     tr.zero_grad()
     pred = torch.empty(coord.shape[0], device=coord.device)
     loss = tr.forward_backward(coord, label, None, pred_out=pred)
@@ -88,6 +88,14 @@ def test_c2_bench_workload_matches_oracle():
     got = _cuda_step(cfg, octree, decoder, coord, label)
     want = _oracle_step(o, dec, coord, label, cfg.sigma_sigmoid)
     print("C2 bench workload:", [int(p.shape[0]) for p in octree.hier_features], compare_step(got, want))
+    # the bench's default form: pool in Morton order, ordered batch, voxel-grouped scatter; every 7th point of a whole-pool
+    # batch (a subsequence of an ordered batch is ordered)
+    pool.sort_morton()
+    coord, label, _ = pool.get_batch(len(pool), gen)
+    coord, label = coord[::7][:100000].contiguous(), label[::7][:100000].contiguous()
+    got = _cuda_step(cfg, octree, decoder, coord, label, morton_ordered=True)
+    want = _oracle_step(o, dec, coord, label, cfg.sigma_sigmoid)
+    print("C2 bench workload, Morton-ordered batch:", compare_step(got, want))
 
 
 @pytest.mark.timeout(900)
