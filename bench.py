@@ -312,6 +312,21 @@ def batches_exceeding_l2(n_points, cap=64):
     return max(4, need) if need <= cap else None
 
 
+def time_graph_steps(graphs, steps, flush_buf, dev):
+    """K replays of the captured whole-step graphs (rotating), CUDA events around every replay -> mean ms per step."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for k in range(steps):
+        if flush_buf is not None:
+            flush_buf.fill_(k & 0xFF)
+        ev[k][0].record()
+        graphs[k % len(graphs)].replay()
+        ev[k][1].record()
+    torch.cuda.synchronize(dev)
+    if flush_buf is None:          # back-to-back replays: first start -> last end, so that nothing between steps is left out
+        return ev[0][0].elapsed_time(ev[-1][1]) / steps
+    return statistics.mean(a.elapsed_time(b) for a, b in ev)
+
+
 def time_steps(trainer, batches, steps, flush_buf, n_norm, dev, all_reduce=True):
     """K steps; flush_buf given: the L2 is flushed before each (untimed 256 MiB write), None: the batches rotate and are
     together larger than L2.  -> per-step (zero+kernel+reduce+allreduce), fused kernel alone, replica
@@ -538,7 +553,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     numa = sdist.pin_to_gpu_numa_node(local) if world > 1 else {"numa_node": sdist.gpu_numa_node(local), "cpus": None}
-    part_info = None
+    part_info, p2p = None, None
     ordered = args.batch_order == "morton"
     if world > 1:
         cfg, octree, decoder, pool, plan, comm, p2p, part_info = build_partitioned_workload(
@@ -577,6 +592,12 @@ def run_ours(args):
     for i in range(max(warm, nb if rotate else 0)):
         step(batches[i % nb])
     torch.cuda.synchronize(dev)
+    graphs = None
+    if not args.eager and (world == 1 or p2p is not None):     # the NCCL route of the exchange is launched eagerly
+        graphs = [trainer.capture_step(b[0], b[1], None, n_norm=n_global, exchange=world > 1) for b in batches]
+        for g_ in graphs[:2]:
+            g_.replay()
+        torch.cuda.synchronize(dev)
 
     # ---- `value`: inputs resident in HBM, CUDA events on the launching stream, L2 flushed between steps ----
     sampler = ClockSampler(local) if rank == 0 else None
@@ -587,12 +608,24 @@ def run_ours(args):
     t_clk0 = time.time()
     if args.cuda_profiler:
         torch.cuda.profiler.start()                   # ncu --profile-from-start off: only the timed steps
-    step_ms, kern_ms, red_ms = time_steps(trainer, batches, args.steps, flush_buf, n_global, dev)
+    # the timed steps: every rotating batch's whole step {grad memset, fused kernel, exchange} captured once as a CUDA graph
+    # (SdfTrainer.capture_step) and replayed -- the host only enqueues graph launches; an eager pass with events between
+    # the phases follows for the kernel / exchange breakdown
+    host_t0 = time.perf_counter()
+    if graphs is not None:
+        step_ms = time_graph_steps(graphs, args.steps, flush_buf, dev)
+        launches = _abi.LAUNCHES["count"] - launches0
+        sdist.barrier(dev)
+        eager_ms, kern_ms, red_ms = time_steps(trainer, batches, args.steps, flush_buf, n_global, dev)
+    else:
+        step_ms, kern_ms, red_ms = time_steps(trainer, batches, args.steps, flush_buf, n_global, dev)
+        eager_ms = step_ms
+        launches = _abi.LAUNCHES["count"] - launches0
     sdist.barrier(dev)
     if args.cuda_profiler:
         torch.cuda.profiler.stop()
-    launches = _abi.LAUNCHES["count"] - launches0
     step_ms = sdist.max_over_ranks(step_ms, dev)
+    eager_ms = sdist.max_over_ranks(eager_ms, dev)
     kern_ms_max = sdist.max_over_ranks(kern_ms, dev)
     red_ms_max = sdist.max_over_ranks(red_ms, dev)
     exch_ms = getattr(time_steps, "last_exchange_ms", 0.0)
@@ -609,7 +642,8 @@ def run_ours(args):
         del tr_r, br
     flushed = None
     if world == 1 and rotate:       # the conservative variant, for the record: everything evicted before every step
-        f_step, f_kern, _ = time_steps(trainer, batches, args.steps, flush_all, n_global, dev)
+        _, f_kern, _ = time_steps(trainer, batches, args.steps, flush_all, n_global, dev)
+        f_step = time_graph_steps(graphs, args.steps, flush_all, dev) if graphs is not None else _
         flushed = {"value": n_global / (f_step * 1e-3), "ms_per_step": f_step, "kernel_ms": f_kern,
                    "l2": "flushed between timed steps (256 MiB write, not timed): tables and gradients come from HBM too"}
     exch_ms_max = sdist.max_over_ranks(exch_ms, dev)
@@ -620,7 +654,10 @@ def run_ours(args):
     # number of collectives.
     n_cont = max(0, min(20000, int(500.0 / max(step_ms, 0.02)) - args.steps))
     for k in range(n_cont):
-        step(batches[k % nb])
+        if graphs is not None:
+            graphs[k % nb].replay()
+        else:
+            step(batches[k % nb])
         if k % 64 == 63:
             torch.cuda.synchronize(dev)
     torch.cuda.synchronize(dev)
@@ -692,7 +729,9 @@ def run_ours(args):
                                        "note": "events around the exchange: its latency + the wait for the slowest rank's kernel"},
                        "kernel_ms_min_over_ranks": kern_ms_min,
                        "l2": l2_note, "l2_flushed": flushed,
-                       "timed_step": "grad memset + fused fwd+loss+bwd kernel + replica fold (+ all-reduce when N>1)"},
+                       "timed_step": "grad memset + fused fwd+loss+bwd kernel (+ replica fold for unordered batches) (+ exchange when N>1)"
+                                     + ("; captured per rotating batch as a CUDA graph (SdfTrainer.capture_step) and replayed" if graphs is not None else "; launched eagerly"),
+                       "eager_ms_per_step": eager_ms},
         # the C2 map (2.75 MB of features) lives in L2: the kernel's physical bound there is the L1TEX LSU data pipe
         # (1 wavefront / clk / SM), not HBM.  wavefronts/point come from the committed ncu capture, time is live.
         "roofline": {"bound": "l1tex_lsu",
@@ -757,6 +796,7 @@ def main():
                     help="order the sampler hands a batch out in (same random index multiset either way)")
     ap.add_argument("--l2", default="rotate", choices=["rotate", "flush"],
                     help="L2 rule of the timed steps: rotate over batches that together exceed L2 (default) or flush before every step")
+    ap.add_argument("--eager", action="store_true", help="launch the timed steps eagerly instead of replaying captured graphs")
     ap.add_argument("--no-hbm-leg", action="store_true")
     ap.add_argument("--hbm-only", action="store_true", help="run only the HBM-bound leg and print its object (ncu target)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -30,7 +30,7 @@ struct shine_p2p {
 namespace {
 
 constexpr int kFlagStride = 128;        // one line per publishing rank
-constexpr int kCtrlOff = 4096;          // {uint32 arrive; uint32 timeouts}
+constexpr int kCtrlOff = 4096;          // {uint32 arrive; uint32 timeouts; uint32 steps done}
 constexpr int kDataOff = 4096 + 256;
 constexpr int kMaxRanks = 16;
 constexpr long long kSpinLimit = 1ll << 24;     // ~0.3 s of polling: a missing peer becomes an error flag, not a hang
@@ -60,8 +60,11 @@ __device__ __forceinline__ float4 ld_peer_f4(const float* p) {
 constexpr int kP2PThreads = 512;
 
 __global__ void __launch_bounds__(kP2PThreads) p2p_exchange_kernel(const __grid_constant__ P2PParams P) {
+    // the step number lives in device memory (control word 2, bumped by the last block of every launch): the launch has no
+    // per-call host state, so a step that contains it can be captured once into a CUDA graph and replayed
+    const uint32_t step = reinterpret_cast<volatile uint32_t*>(P.peer[P.rank] + kCtrlOff)[2] + 1u;
     unsigned char* mine_base = P.peer[P.rank];
-    float* mine = data_of(mine_base, P.step, P.max_floats);
+    float* mine = data_of(mine_base, step, P.max_floats);
     const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gs = (int64_t)gridDim.x * blockDim.x;
     const int lp = P.feature_dim >> 2;
 
@@ -83,19 +86,20 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_exchange_kernel(const __grid_
     __syncthreads();
     if (gridDim.x == 1) {
         is_last = 1;
+        if (threadIdx.x == 0) ctrl[2] = step;                           // every thread of the block has read it (barrier above)
     } else {
         if (threadIdx.x == 0) {
             __threadfence();
             const uint32_t prev = atomicAdd(const_cast<uint32_t*>(ctrl), 1u);
             __threadfence();                                              // acquire side of the hand-shake for the last block
             is_last = prev == gridDim.x - 1;
-            if (is_last) ctrl[0] = 0u;                                    // ready for the next launch
+            if (is_last) { ctrl[0] = 0u; ctrl[2] = step; }              // every block has arrived, i.e. has read the step
         }
         __syncthreads();
     }
     if (is_last && threadIdx.x < P.nranks) {        // st.release.sys orders everything the barrier made visible to this thread
         uint32_t* flag = reinterpret_cast<uint32_t*>(P.peer[threadIdx.x] + (size_t)P.rank * kFlagStride);
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(P.step) : "memory");
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(step) : "memory");
     }
     // while the publication travels: which of this thread's exchange-buffer quads does the rank hold, and which ranks
     // contribute to them (local reads only).  Up to kItems quads per thread; the launch sizes the grid so that this covers
@@ -131,7 +135,7 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_exchange_kernel(const __grid_
         do {
             asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
             if (++spin > kSpinLimit) { atomicAdd(const_cast<uint32_t*>(ctrl) + 1, 1u); break; }
-        } while ((int32_t)(seen - P.step) < 0);
+        } while ((int32_t)(seen - step) < 0);
     }
     __syncthreads();
     // 4. reduce in place, fixed rank order (bitwise identical on every rank).  Only the ranks that hold a row of the corner
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_exchange_kernel(const __grid_
             for (int r = 0; r < 8; ++r) {
                 v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (base + r < P.nranks && ((m >> (base + r)) & 1u))
-                    v[r] = ld_peer_f4(data_of(P.peer[base + r], P.step, P.max_floats) + fo);
+                    v[r] = ld_peer_f4(data_of(P.peer[base + r], step, P.max_floats) + fo);
             }
 #pragma unroll
             for (int r = 0; r < 8; ++r) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(kP2PThreads) p2p_exchange_kernel(const __grid_
         for (int r = 0; r < 8; ++r) {
             va[r] = make_float4(0.f, 0.f, 0.f, 0.f); vb[r] = va[r];
             if (r < P.nranks) {
-                const float* base = data_of(P.peer[r], P.step, P.max_floats);
+                const float* base = data_of(P.peer[r], step, P.max_floats);
                 if ((from[0] >> r) & 1u) va[r] = ld_peer_f4(base + fa);
                 if ((from[1] >> r) & 1u) vb[r] = ld_peer_f4(base + fb);
             }
@@ -258,8 +262,8 @@ int shine_p2p_exchange(shine_p2p* ctx, float* dec_grads, int64_t dec_floats, con
     const int64_t most = end / 4;
     for (int r = 0; r < kMaxRanks; ++r) P.peer[r] = r < ctx->nranks ? ctx->peer[r] : nullptr;
     for (int r = 0; r < ctx->nranks; ++r) if (!P.peer[r]) return SHINE_ERR_INVALID_ARG;      // connect() first
-    ctx->step += 1;
-    P.nranks = ctx->nranks; P.rank = ctx->rank; P.step = ctx->step; P.max_floats = ctx->max_floats; P.dec_floats = dec_floats;
+    ctx->step += 1;                     // bookkeeping only (launches issued); the protocol's step number is on the device
+    P.nranks = ctx->nranks; P.rank = ctx->rank; P.step = 0; P.max_floats = ctx->max_floats; P.dec_floats = dec_floats;
     P.dec = dec_grads; P.num_levels = num_levels; P.feature_dim = feature_dim;
     DeviceGuard guard(ctx->local);
     // latency-bound: every thread should own at most two quads of the buffer, so that the reduce is ONE NVLink round trip

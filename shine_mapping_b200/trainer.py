@@ -289,6 +289,50 @@ class SdfTrainer:
 
     # ---- pipelined host-buffer entry ------------------------------------------------------------------------
 
+    class StepGraph:
+        """One whole step on device tensors as a CUDA graph (see `capture_step`)."""
+
+        def __init__(self, trainer, graph, launches):
+            self.trainer, self.graph, self.launches = trainer, graph, launches
+
+        def replay(self):
+            self.graph.replay()
+            self.trainer._loss_clean = False
+            _abi.LAUNCHES["count"] += self.launches       # the replayed kernels are this library's launches too
+            return self.trainer.loss
+
+    def capture_step(self, coord, sdf_label, weight=None, n_norm=None, exchange: bool = True, optimizer: bool = False):
+        """{zero gradients -> fused fwd + loss + bwd -> the multi-GPU exchange (-> Adam)} on DEVICE tensors, captured once
+        as a CUDA graph: `replay()` re-runs it on whatever the tensors hold then, without the host in the loop (the
+        peer-memory exchange keeps its step number on the device for this).  One real step runs as warm-up before the
+        capture: with several ranks every rank has to call this the same number of times."""
+        self._sync()
+        dev = coord.device
+
+        def body():
+            self.zero_grad()
+            self.forward_backward(coord, sdf_label, weight, n_norm=n_norm)
+            if exchange:
+                self.all_reduce_grads()
+            if optimizer:
+                self.optimizer_step(zero_grad=False, device_step=True)
+
+        if optimizer:
+            self._sync_adam_state()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        before = _abi.LAUNCHES["count"]
+        with torch.cuda.graph(graph):
+            body()
+        launches = _abi.LAUNCHES["count"] - before
+        _abi.LAUNCHES["count"] = before                  # capturing launched nothing
+        return SdfTrainer.StepGraph(self, graph, launches)
+
     class HostStepHandle:
         """Result of `submit_host_step`: `.result()` blocks until that step's loss is on the host."""
 

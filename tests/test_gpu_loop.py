@@ -210,3 +210,24 @@ def test_incremental_loop_runs(built_lib):
     assert hist[2]["rows"][-1] > hist[0]["rows"][-1]                       # the map grew
     assert not any(p.requires_grad for p in decoder.parameters())          # frozen after frame 2
     assert all(w.abs().sum() > 0 for w in octree.importance_weight)
+
+
+def test_capture_step_replays_the_eager_step():
+    """SdfTrainer.capture_step: the graph re-runs {zero, fused step} on whatever the captured tensors hold at replay time
+    and gives what the eager calls give (same kernels: gradients equal up to atomics order)."""
+    from shine_mapping_b200 import SdfTrainer
+    case = make_case(n_points=2500, n_batch=4000, feat_levels=3, seed=31)
+    cfg, octree, dec = build_cuda_models(case, DEV)
+    tr = SdfTrainer(cfg, octree, dec)
+    coord = torch.from_numpy(case["coord"]).to(DEV); label = torch.from_numpy(case["label"]).to(DEV)
+    graph = tr.capture_step(coord, label, None, exchange=False)
+    perm = torch.randperm(coord.shape[0], device=DEV)
+    for data in ((coord.clone(), label.clone()), (coord[perm] * 0.999, label[perm])):
+        coord.copy_(data[0]); label.copy_(data[1])
+        graph.replay(); torch.cuda.synchronize()
+        got_loss, got = float(tr.loss), [g.clone() for g in tr.table_grads] + [g.clone() for g in tr.dec_grads if g is not None]
+        tr.zero_grad(); tr.forward_backward(coord, label, None); torch.cuda.synchronize()
+        want = list(tr.table_grads) + [g for g in tr.dec_grads if g is not None]
+        assert abs(got_loss - float(tr.loss)) <= 1e-6 * abs(float(tr.loss))
+        for a, b in zip(got, want):
+            assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()) + 1e-12

@@ -122,6 +122,17 @@ def _nccl_worker(rank, world, port, out_dir):
         torch.cuda.synchronize()
         check_rank_against_global([g.detach().cpu().numpy() for g in tr2.table_grads], keys, key_to_row, res_glob)
         _check_decoder_and_loss(tr2, float(loss2), res_glob)
+    # the whole step {zero, fused kernel, peer-memory exchange} captured as a CUDA graph and replayed: the exchange keeps
+    # its step number on the device, so replays keep the protocol going (four replays: both buffer parities twice)
+    cd, ld = batch[0][m].to(dev), batch[1][m].to(dev)
+    graph = tr2.capture_step(cd, ld, None, n_norm=batch[0].shape[0], exchange=True)
+    for _ in range(4):
+        graph.replay()
+        torch.cuda.synchronize()
+        check_rank_against_global([g.detach().cpu().numpy() for g in tr2.table_grads], keys, key_to_row, res_glob)
+        loss3 = tr2.loss.detach().clone()
+        comm.all_reduce(loss3.view(1))
+        _check_decoder_and_loss(tr2, float(loss3), res_glob)
     assert p2p.timeouts() == 0
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     dist.barrier()
