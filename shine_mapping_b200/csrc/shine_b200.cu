@@ -43,6 +43,15 @@
 #ifndef SHINE_SLOT_PREFETCH
 #define SHINE_SLOT_PREFETCH 0  // training kernel: hash + L1 prefetch of the NEXT tile's home slots before this tile's scatter
 #endif
+#ifndef SHINE_ZERO_TILE_SKIP
+#define SHINE_ZERO_TILE_SKIP 1   // tiles whose 16 points miss every level: prediction of the zero feature vector, decoder gradients by linearity
+#endif
+#ifndef SHINE_DYNAMIC_TILES
+#define SHINE_DYNAMIC_TILES 0    // 1: warps draw their tiles from a device counter (measured slower: concurrent warps then share rows)
+#endif
+#ifndef SHINE_PERMUTE_TILES
+#define SHINE_PERMUTE_TILES 0    // 1: multiplicative permutation of the tile order (measured slower: a block loses its adjacent tiles)
+#endif
 #ifndef SHINE_EXPERIMENT_NO_RED
 #define SHINE_EXPERIMENT_NO_RED 0
 #endif
@@ -545,6 +554,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
 
     constexpr bool kSectorProbe = TRAIN ? (SHINE_SECTOR_PROBE_TRAIN != 0) : (SHINE_SECTOR_PROBE_INFER != 0);
     constexpr bool kSlotPrefetch = TRAIN && !kSectorProbe && (SHINE_SLOT_PREFETCH != 0) && (SHINE_CPASYNC_PREFETCH == 0);
+    constexpr bool kZeroSkip = (SHINE_ZERO_TILE_SKIP != 0) && (SHINE_CPASYNC_PREFETCH == 0);
     const bool poly = P.oct.poly_interp != 0;
     const int L = P.oct.num_levels;
     const float up = (TRAIN && P.d_loss) ? __ldg(P.d_loss) : 1.0f;
@@ -608,6 +618,14 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         }
     };
 
+    // sequence number of a warp's work item -> tile index (identity, or a multiplicative permutation of the tiles)
+    auto tile_of = [&](int seq) -> int {
+        if constexpr (SHINE_PERMUTE_TILES != 0)
+            return (P.tile_perm_mul > 1 && seq < P.num_tiles) ? (int)(((long long)seq * P.tile_perm_mul) % P.num_tiles) : seq;
+        else
+            return seq;
+    };
+
 #if SHINE_CPASYNC_PREFETCH
     // software pipeline, depth 1: the next tile's coordinates / label / weight travel global -> shared memory with
     // cp.async (no registers pinned, nothing to spill) while this tile computes
@@ -654,7 +672,7 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
     float nx = 0.f, ny = 0.f, nz = 0.f, nlab = 0.f, nwgt = 1.f;
     bool nvalid = false;
     auto prefetch_inputs = [&](int tl) {
-        const int64_t p = (int64_t)tl * kTile + g + 8 * odd;
+        const int64_t p = (int64_t)tile_of(tl) * kTile + g + 8 * odd;
         nvalid = tl < P.num_tiles && p < P.n;
         if (nvalid) {
             nx = __ldg(P.coord + 3 * p); ny = __ldg(P.coord + 3 * p + 1); nz = __ldg(P.coord + 3 * p + 2);
@@ -665,12 +683,69 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
     prefetch_inputs(warp_global);
     if (kSlotPrefetch) stage_slots(nvalid, nx, ny, nz);   // first tile
 
-    for (int tile = warp_global; tile < P.num_tiles; tile += warp_stride) {
+    // Zero-tile shortcut (kZeroSkip).  A point that misses every level has the feature vector 0, so every such point gets the
+    // SAME prediction pred0 = Decoder.sdf(0), and its decoder gradients are dL/dpred times the gradients of that one forward:
+    // linear in dL/dpred.  In a Morton-ordered batch free-space samples fill whole tiles (35 % of the C2 tiles): such a tile
+    // only walks the hash, evaluates its loss terms against pred0 and adds its dL/dpred to a sum.  Pass 0 of the loop below
+    // is one virtual tile (no points: features 0) run through the forward to get pred0; after the block's real tiles, warp 0
+    // runs one more virtual tile whose first point carries the block's dL/dpred sum through the ordinary backward.
+    int phase = kZeroSkip ? 0 : 1;          // 0: virtual forward, 1: this warp's tiles, 2: virtual backward (warp 0)
+    bool advance = false, last_pass = false;
+    float pred0 = 0.f, zsum = 0.f;
+    auto bce_point = [&](float pv, float lb, float wg, float& li, float& dp) {
+        // MUFU-based exp / log / reciprocal (~2 ulp): |d loss| <~ 1e-7, far inside the 2e-5 parity tolerance
+        const float zt = __fdividef(1.0f, 1.0f + __expf(-__fdividef(lb, P.sigma)));   // sigmoid(label / sigma)
+        const float e = __expf(-fabsf(pv));
+        li = fmaxf(pv, 0.f) - pv * zt + __logf(1.0f + e);                               // log1p(e), e in (0, 1]
+        dp = 0.f;
+        if (TRAIN) {
+            const float rs = __fdividef(1.0f, 1.0f + e);
+            const float sg = pv >= 0.f ? rs : e * rs;                                   // sigmoid(pred)
+            dp = (sg - zt) * wg * gscale;
+        }
+    };
+    // tile schedule: the first tile of a warp is its global index; every further one is drawn from P.tile_counter (counter
+    // value k <-> tile warp_stride + k), requested a whole tile ahead so that the atomic's latency is never waited for
+    const bool dynamic = (SHINE_DYNAMIC_TILES != 0) && P.tile_counter != nullptr;
+    int next_tile = 0, pending = 0;
+    if (dynamic && lane == 0) pending = atomicAdd(P.tile_counter, 1);
+    for (int seq = warp_global;; seq = !advance ? seq : (dynamic ? next_tile : seq + warp_stride)) {
+        if (last_pass) break;
+        const int tile = tile_of(seq);
+        if (phase == 1 && seq >= P.num_tiles) {
+            if constexpr (kZeroSkip && DEC_GRAD) {
+                // hand the all-miss dL/dpred sums of the block's warps to warp 0 (every warp passes here exactly once)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) zsum += __shfl_xor_sync(kFull, zsum, o);
+                if (lane == 0) smem[SmemPlan::PRE + warp] = zsum;
+                __syncthreads();
+                if (warp != 0) break;
+                float tot = 0.f;
+#pragma unroll
+                for (int w = 0; w < kWarps; ++w) tot += smem[SmemPlan::PRE + w];
+                if (tot == 0.f) break;
+                zsum = tot;
+                phase = 2;
+            } else {
+                break;
+            }
+        }
+        const bool virt = phase != 1;
+        last_pass = phase == 2;
+        advance = !virt;
         const int64_t base = (int64_t)tile * kTile;
         const int64_t myp = base + g + 8 * odd;
-        const bool valid = nvalid;
+        const bool valid = virt ? false : nvalid;
         const float x = nx, y = ny, z = nz, lab = nlab, wgt = nwgt;
-        prefetch_inputs(tile + warp_stride);
+        if (!virt) {
+            if (dynamic) {
+                next_tile = warp_stride + __shfl_sync(kFull, pending, 0);
+                prefetch_inputs(next_tile);
+                if (lane == 0) pending = atomicAdd(P.tile_counter, 1);
+            } else {
+                prefetch_inputs(seq + warp_stride);
+            }
+        }
 
 #endif
         float feat[4];
@@ -832,6 +907,20 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
             }
         }
         }
+#if !SHINE_CPASYNC_PREFETCH
+        if (kZeroSkip && phase == 1 && __ballot_sync(kFull, hitmask != 0u) == 0u) {
+            // no point of this tile sees a node on any level: features 0, prediction pred0, no table gradient; the decoder
+            // gradients follow by linearity from the sum of dL/dpred (virtual backward tile at the end of the block)
+            if (!TRAIN && P.mask && half == 0 && valid) P.mask[myp] = 0;
+            if (P.pred && half == 0 && valid) P.pred[myp] = pred0;
+            if (P.label != nullptr && valid) {
+                float li, dpz;
+                bce_point(pred0, lab, wgt, li, dpz);
+                if (half == 0) { loss_acc += wgt * li; zsum += dpz; }
+            }
+            continue;
+        }
+#endif
         if (TRAIN && !GROUPED) {
             if (kPark == 16) tmem_st16(tpark, pk); else tmem_st32(tpark, pk);
             if (kIdPark == 16) tmem_st16(tpark + kPark, idp); else tmem_st32(tpark + kPark, idp);
@@ -919,6 +1008,9 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         const float b3 = smem[SmemPlan::B3];
         p0 += b3; p8 += b3;
         const float pown = odd ? p8 : p0;
+#if !SHINE_CPASYNC_PREFETCH
+        if (kZeroSkip && phase == 0) { pred0 = pown; phase = 1; continue; }     // the virtual forward: every row is Decoder.sdf(0)
+#endif
         if (P.pred && half == 0 && valid) P.pred[myp] = pown;
 
         if (P.label == nullptr) continue;   // pure inference
@@ -926,7 +1018,11 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
         // ---- sdf_bce_loss (utils/loss.py:17-24) + dL/dpred ---------------------------------------------
         float dpo = 0.f;
         if (valid) {
-            // MUFU-based exp / log / reciprocal (~2 ulp): |d loss| <~ 1e-7, far inside the 2e-5 parity tolerance
+#if !SHINE_CPASYNC_PREFETCH
+            float li;
+            bce_point(pown, lab, wgt, li, dpo);
+            if (half == 0) loss_acc += wgt * li;
+#else
             const float zt = __fdividef(1.0f, 1.0f + __expf(-__fdividef(lab, P.sigma)));   // sigmoid(label / sigma)
             const float e = __expf(-fabsf(pown));
             const float li = fmaxf(pown, 0.f) - pown * zt + __logf(1.0f + e);              // log1p(e), e in (0, 1]
@@ -936,8 +1032,12 @@ __global__ void __launch_bounds__(256, TRAIN ? SHINE_TRAIN_MINB : SHINE_INFER_MI
                 const float sg = pown >= 0.f ? rs : e * rs;                               // sigmoid(pred)
                 dpo = (sg - zt) * wgt * gscale;
             }
+#endif
         }
         if (!TRAIN) continue;
+#if !SHINE_CPASYNC_PREFETCH
+        if (kZeroSkip && phase == 2) dpo = (g == 0 && odd == 0) ? zsum : 0.f;   // point 0 of the virtual tile carries the block's sum
+#endif
 
         // ---- backward: MLP dgrad on tensor cores ------------------------------------------------------
         const float dpx = __shfl_xor_sync(kFull, dpo, 1);
@@ -1548,7 +1648,36 @@ int launch_fused_t(const StepParams& P, cudaStream_t st) {
     int grid = sm_count() * per_sm;
     if (grid > blocks_needed) grid = blocks_needed;
     if (grid < 1) grid = 1;
-    kern<<<grid, 256, smem_bytes, st>>>(P);
+    // dynamic tile schedule: the warps draw tile indices from a device counter (tiles differ a lot in cost once whole tiles
+    // of free-space samples take the zero-tile shortcut).  A small ring of counters per device: a launch zeroes its own.
+    StepParams Q = P;
+    Q.tile_counter = nullptr;
+    Q.tile_perm_mul = 0;
+#if SHINE_PERMUTE_TILES
+    if (P.num_tiles > 4 * grid * 8) {        // several rounds of tiles per warp: decorrelate what an SM gets from the batch order
+        auto gcd = [](long long a, long long b) { while (b) { const long long t = a % b; a = b; b = t; } return a; };
+        long long m = (long long)(0.6180339887 * (double)P.num_tiles) | 1;
+        while (gcd(m, P.num_tiles) != 1) m += 2;
+        Q.tile_perm_mul = (int32_t)m;
+    }
+#endif
+#if SHINE_DYNAMIC_TILES
+    {
+        static int32_t* ring_by_dev[kMaxDevices] = {nullptr};
+        static unsigned next_by_dev[kMaxDevices] = {0};
+        constexpr unsigned kRing = 64;
+        const int dev = current_device();
+        if (!ring_by_dev[dev]) {
+            e = cudaMalloc(reinterpret_cast<void**>(&ring_by_dev[dev]), kRing * 64);      // one 64-byte line per counter
+            if (e != cudaSuccess) return (int)e;
+        }
+        int32_t* ctr = ring_by_dev[dev] + 16 * (next_by_dev[dev]++ % kRing);
+        e = cudaMemsetAsync(ctr, 0, sizeof(int32_t), st);
+        if (e != cudaSuccess) return (int)e;
+        Q.tile_counter = ctr;
+    }
+#endif
+    kern<<<grid, 256, smem_bytes, st>>>(Q);
     return (int)cudaGetLastError();
 }
 
@@ -1599,7 +1728,7 @@ int fill_params(StepParams& P, const shine_octree* oct, const shine_decoder* dec
     P.oct = *oct; P.dec = *dec; P.coord = coord; P.n = n;
     P.num_tiles = (int32_t)((n + kTile - 1) / kTile);
     P.label = nullptr; P.weight = nullptr; P.d_loss = nullptr; P.pred = nullptr; P.loss = nullptr; P.mask = nullptr;
-    P.mask_level = 0; P.sigma = 1.f; P.loss_scale = 1.f; P.weighted = 0; P.debug_dx = nullptr;
+    P.mask_level = 0; P.sigma = 1.f; P.loss_scale = 1.f; P.weighted = 0; P.debug_dx = nullptr; P.tile_counter = nullptr; P.tile_perm_mul = 0;
     return SHINE_OK;
 }
 

@@ -43,6 +43,7 @@ class SdfTrainer:
         self.p2p = p2p              # dist.P2PExchange: the spatial exchange as one NVLink peer-memory kernel
         # gradient replicas for small hot levels (see FeatureOctree._replicas_for); on by default for big batches
         self.use_replicas = os.environ.get("SHINE_FUSED_REPLICAS", "1") != "0"
+        self.grouped_replicas = os.environ.get("SHINE_GROUPED_REPLICAS", "0") != "0"   # replicas for ordered batches too (A/B)
         self.group = process_group
         self.morton_ordered = bool(morton_ordered)   # default for every step: batches come from a Morton-sorted SamplePool
         self.tf32x1 = tf32x1
@@ -134,7 +135,7 @@ class SdfTrainer:
         scale = 1.0 if cfg.loss_reduction == "sum" else 1.0 / float(n_norm if n_norm else n)
         # gradient replicas spread same-row atomics of unordered batches; the grouped scatter of ordered batches issues one
         # red per run and row, so it goes straight to the gradient table (and there is no fold kernel)
-        replicas = self.use_replicas and not (flags & _abi.FLAG_MORTON_ORDERED)
+        replicas = self.use_replicas and (self.grouped_replicas or not (flags & _abi.FLAG_MORTON_ORDERED))
         od = self.octree._descriptor(None, self.table_grads, n_points=n if replicas else 0)
         dd = self.decoder.c_descriptor(self.dec_grads if self._dec_trainable else None)
         if not accumulate_loss and not self._loss_clean:

@@ -62,6 +62,46 @@ def test_grouped_scatter_matches_oracle(levels, poly, weighted, reduction, order
     print(compare_step(run_cuda_step(case, DEV, morton_ordered=True, freeze_decoder=True), want_f))
 
 
+@pytest.mark.parametrize("ordered,weighted,reduction,frozen", [(True, False, "mean", False), (False, True, "sum", False),
+                                                              (True, True, "mean", True)])
+def test_all_miss_tiles_match_oracle(ordered, weighted, reduction, frozen):
+    """Whole 16-point tiles of free-space samples that miss every level (a third of the tiles of an ordered C2 batch): the
+    kernel gives them Decoder.sdf(0) and folds their decoder gradients in by linearity.  Loss, predictions and every
+    gradient must equal the oracle's, with the block of far points in the middle of a batch (order drawn) and spread by
+    the Morton sort (ordered), general and grouped kernels, weighted / sum, and with a frozen decoder."""
+    case = make_case(n_points=2500, n_batch=1500, feat_levels=3, seed=91, weighted=weighted, reduction=reduction)
+    rng = np.random.default_rng(7)
+    far = np.concatenate([rng.uniform(0.55, 0.95, size=(700, 3)), rng.uniform(-0.95, -0.6, size=(420, 3))]).astype(np.float32)
+    k = 640                                     # a tile-aligned block of far points inside the batch
+    case["coord"] = np.concatenate([case["coord"][:k], far, case["coord"][k:]]).astype(np.float32)
+    case["label"] = np.concatenate([case["label"][:k], rng.uniform(-0.2, 0.2, size=far.shape[0]).astype(np.float32),
+                                    case["label"][k:]])
+    case["weight"] = np.concatenate([case["weight"][:k], rng.uniform(0.5, 1.5, size=far.shape[0]).astype(np.float32),
+                                     case["weight"][k:]])
+    if ordered:
+        case = sort_case_morton(case)
+    want = run_oracle_step(case)
+    missed_everywhere = np.logical_and.reduce([(idx == -1).all(axis=1) for idx in want["indices"]])
+    assert int(missed_everywhere.sum()) >= far.shape[0]                     # the far points really miss every level
+    if not ordered:
+        assert bool(missed_everywhere[k:k + far.shape[0]].all())
+    if frozen:
+        want = dict(want); want["dec_grads"] = {}
+    for flag in (False, True):
+        print(compare_step(run_cuda_step(case, DEV, morton_ordered=flag, freeze_decoder=frozen), want))
+
+
+def test_all_miss_batch():
+    """Every point misses every level: only virtual tiles reach the decoder."""
+    case = make_case(n_points=2500, n_batch=64, feat_levels=2, seed=93)
+    rng = np.random.default_rng(3)
+    n = 1000
+    case["coord"] = rng.uniform(0.6, 0.9, size=(n, 3)).astype(np.float32)
+    case["label"] = rng.uniform(-0.1, 0.1, size=n).astype(np.float32)
+    case["weight"] = np.ones(n, dtype=np.float32)
+    print(compare_step(run_cuda_step(case, DEV), run_oracle_step(case)))
+
+
 def test_grouped_scatter_dense_runs():
     """Many samples per voxel (16-point tiles inside ONE node at every level, runs crossing tile borders)."""
     case = make_case(n_points=2500, n_batch=64, feat_levels=3, seed=77)
