@@ -113,7 +113,8 @@ def build_partitioned_workload(device, rank, world, n_azimuth, n_frames=None, ex
 
 BATCH_ORDER_NOTE = {
     "morton": "randint-drawn samples (with replacement, the reference's sampler) handed out in Morton order of their "
-              "coordinates (SamplePool.sort_morton + sorted indices); the loss of a batch does not depend on its order",
+              "coordinates, free-space samples (no octree node on any level) behind the others (SamplePool.sort_morton + "
+              "sorted indices); the loss of a batch does not depend on its order",
     "random": "randint-drawn samples in the order drawn (the reference's order)"}
 
 
@@ -567,7 +568,7 @@ def run_ours(args):
         n = len(pool) if args.points <= 0 else args.points
         trainer = SdfTrainer(cfg, octree, decoder, shard_mode="spatial", morton_ordered=ordered)
     if ordered:
-        pool.sort_morton()      # once, with the map; batches are then handed out in Morton order
+        pool.sort_morton(octree=octree)      # once, with the map: Morton order, free-space samples (no node on any level) last
     n_global = n * world
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     # L2 rule: inputs larger than L2 (default) -- the timed steps rotate over batches that together exceed the 126 MB L2 by

@@ -300,6 +300,21 @@ class FeatureOctree(nn.Module):
         sample_points_with_morton = torch.hstack((sample_points, points_morton.view(-1, 1)))
         return sample_points_with_morton, set(points_morton.cpu().numpy())
 
+    @torch.no_grad()
+    def sees_a_node(self, coord: torch.Tensor) -> torch.Tensor:
+        """bool [N]: does the point fall into a node of ANY featured level?  Every leaf node has all its ancestors
+        (update() derives the coarser node sets from the leaf keys, reference :129-143), so this is a lookup at the
+        coarsest featured level.  Plain torch (sorted keys + searchsorted) on whatever device the octree lives on: a
+        set-up-time helper for the sample pool (`SamplePool.sort_morton(octree=...)`), not part of the step."""
+        lvl = self.free_level_num
+        keys = self._levels[lvl].node_keys
+        if keys.numel() == 0:
+            return torch.zeros(coord.shape[0], dtype=torch.bool, device=coord.device)
+        table = torch.sort(keys.to(coord.device)).values
+        q = points_to_morton(quantize_points(coord, lvl))
+        pos = torch.searchsorted(table, q).clamp_(max=table.numel() - 1)
+        return table[pos] == q
+
     def get_octree_nodes(self, level):
         """Node centres at `level` in the [-1,1] cube (reference :94-101)."""
         nodes = morton_to_points(self._levels[level].node_keys).cpu().numpy()

@@ -120,11 +120,18 @@ class SamplePool:
     def __len__(self):
         return self.sdf_label_pool.shape[0]
 
-    def sort_morton(self, level: int = 16):
-        """Reorder the pool along the Z-order curve of a 2^level grid over [-1, 1]^3 (16: kaolin's int16 coordinates)."""
+    def sort_morton(self, level: int = 16, octree=None):
+        """Reorder the pool along the Z-order curve of a 2^level grid over [-1, 1]^3 (16: kaolin's int16 coordinates).
+        With `octree` (the map the pool belongs to) the samples that see no node on any level — free space: their features
+        are 0 whatever the tables hold — go behind all others, each part in Z-order: the tiles of a batch that take the
+        step kernel's zero-tile shortcut then sit at the end of the batch, where the kernel's strided tile schedule hands
+        every warp the same share of them."""
         from .feature_octree import points_to_morton, quantize_points
         if len(self):
-            order = torch.argsort(points_to_morton(quantize_points(self.coord_pool, level)))
+            key = points_to_morton(quantize_points(self.coord_pool, level))
+            if octree is not None:
+                key = key | ((~octree.sees_a_node(self.coord_pool)).long() << 62)      # Morton keys use 48 bits
+            order = torch.argsort(key)
             self.coord_pool = self.coord_pool[order].contiguous()
             self.sdf_label_pool = self.sdf_label_pool[order].contiguous()
             self.weight_pool = self.weight_pool[order].contiguous()

@@ -241,3 +241,39 @@ def test_sample_pool_morton_order_keeps_the_sampler_and_orders_the_batch():
     assert not torch.equal(l, l2)
     pool.append(coord[:3], torch.zeros(3), torch.ones(3))
     assert pool.ordered is False                                              # appending breaks the order until re-sorted
+
+
+def test_free_space_samples_go_last_and_sees_a_node_matches_the_node_tables():
+    """FeatureOctree.sees_a_node == membership in the coarsest featured level's node dict (every leaf has its ancestors);
+    SamplePool.sort_morton(octree=...) puts the samples without any node behind the others, both parts in Z-order, and a
+    batch inherits that layout."""
+    from shine_mapping_b200 import FeatureOctree, synth
+    from shine_mapping_b200.feature_octree import points_to_morton, quantize_points
+    case = make_case(n_points=2500, n_batch=4000, feat_levels=3, seed=17)
+    cfg = make_config(3, device="cpu")
+    octree = FeatureOctree(cfg)
+    for fr in case["frames"]:
+        octree.update(torch.from_numpy(np.asarray(fr)))
+    coord = torch.from_numpy(case["coord"])
+    seen = octree.sees_a_node(coord)
+    lvl = octree.free_level_num
+    table = octree.nodes_lookup_tables[lvl]
+    keys = points_to_morton(quantize_points(coord, lvl)).tolist()
+    assert seen.tolist() == [k in table for k in keys]
+    finer = octree.nodes_lookup_tables[octree.max_level]
+    leaf_keys = points_to_morton(quantize_points(coord, octree.max_level)).tolist()
+    assert all(s for s, k in zip(seen.tolist(), leaf_keys) if k in finer)       # a leaf hit implies a coarse hit
+    assert 0 < int(seen.sum()) < len(seen)
+    pool = synth.SamplePool("cpu")
+    pool.append(coord, torch.from_numpy(case["label"]), torch.from_numpy(case["weight"]))
+    pool.sort_morton(octree=octree)
+    s2 = octree.sees_a_node(pool.coord_pool)
+    n_near = int(s2.sum())
+    assert bool(s2[:n_near].all()) and not bool(s2[n_near:].any())
+    for part in (pool.coord_pool[:n_near], pool.coord_pool[n_near:]):
+        k = points_to_morton(quantize_points(part, 16))
+        assert bool((k[1:] >= k[:-1]).all())
+    c, _, _ = pool.get_batch(1000, torch.Generator().manual_seed(2))
+    sb = octree.sees_a_node(c)
+    nb = int(sb.sum())
+    assert bool(sb[:nb].all()) and not bool(sb[nb:].any())

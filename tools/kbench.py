@@ -16,6 +16,7 @@ ap.add_argument("--leaf-vox", type=float, default=0.2)
 ap.add_argument("--step-m", type=float, default=2.0)
 ap.add_argument("--sorted", action="store_true", help="Morton-sort the batch (locality experiment)")
 ap.add_argument("--quick", action="store_true", help="only the step / frozen / infer lines")
+ap.add_argument("--free-last", action="store_true", help="with --sorted: samples that see no node go behind all others")
 args = ap.parse_args()
 dev = torch.device("cuda", 0)
 from shine_mapping_b200 import Decoder, FeatureOctree, synth
@@ -29,7 +30,10 @@ gen = torch.Generator(device=dev).manual_seed(1)
 coord, label, weight = pool.get_batch(n, gen)
 if args.sorted:
     from shine_mapping_b200.feature_octree import points_to_morton, quantize_points
-    order = torch.argsort(points_to_morton(quantize_points(coord, 12)))
+    key = points_to_morton(quantize_points(coord, 12))
+    if args.free_last:
+        key = key | ((~octree.sees_a_node(coord)).long() << 62)
+    order = torch.argsort(key)
     coord, label, weight = coord[order].contiguous(), label[order].contiguous(), weight[order].contiguous()
 print(f"table MB={sum(p.numel() for p in octree.hier_features)*4/1e6:.1f}", end=" "); print(f"N={n} rows={[int(p.shape[0]) for p in octree.hier_features]} pool={len(pool)}")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
